@@ -1,0 +1,195 @@
+"""Thin tensor-level wrappers over the C ABI: torch is used for device memory and streams only.
+
+Every function takes CUDA torch tensors (contiguous, float32 / int32 / int64 as documented in include/apr_b200.h),
+enqueues on the current torch stream and returns torch tensors.  No function here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STREAM_INIT = 0x494E4931
+STREAM_ADV = 0x41445631
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("apr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None) -> int:
+    if t is None:
+        return 0
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def device_info() -> Tuple[int, int, int]:
+    a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.lib().apr_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def init_truncated_normal(W: torch.Tensor, stddev: float, seed: int, table_id: int, tag: int = STREAM_INIT) -> None:
+    rows, d = W.shape
+    _lib.check(_lib.lib().apr_init_truncated_normal(_ptr(W, torch.float32), rows, d, float(stddev), seed & 0xFFFFFFFF,
+                                                    table_id & 0xFFFFFFFF, tag, _stream()))
+
+
+def fill(x: torch.Tensor, value: float) -> None:
+    _lib.check(_lib.lib().apr_fill_f32(_ptr(x, torch.float32), x.numel(), float(value), _stream()))
+
+
+def sample_epoch(pairs_u: torch.Tensor, pairs_i: torch.Tensor, batch: int, num_items: int, csr_ptr: torch.Tensor,
+                 csr_idx: torch.Tensor, seed: int, epoch: int, dns: int = 1):
+    """-> (u[S,B], i[S,B], u_dns[S,B*dns], j[S,B*dns]) int32 device tensors (APR.py:39-81)."""
+    n = pairs_u.numel()
+    S = n // batch
+    if S < 1:
+        raise ValueError("fewer training pairs than one batch")
+    dev = pairs_u.device
+    u = torch.empty((S, batch), dtype=torch.int32, device=dev)
+    i = torch.empty((S, batch), dtype=torch.int32, device=dev)
+    ud = torch.empty((S, batch * dns), dtype=torch.int32, device=dev)
+    j = torch.empty((S, batch * dns), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().apr_sample_epoch(_ptr(pairs_u, torch.int32), _ptr(pairs_i, torch.int32), n, batch, num_items,
+                                           _ptr(csr_ptr, torch.int64), _ptr(csr_idx, torch.int32) if csr_idx.numel() else 0,
+                                           csr_ptr.numel() - 1, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, dns, _ptr(u), _ptr(i),
+                                           _ptr(ud), _ptr(j), _ptr(err), _stream()))
+    return u, i, ud, j, err
+
+
+def select_dns(P: torch.Tensor, Q: torch.Tensor, u_dns: torch.Tensor, j_dns: torch.Tensor, dns: int) -> torch.Tensor:
+    n_pos = u_dns.numel() // dns
+    out = torch.empty(n_pos, dtype=torch.int32, device=P.device)
+    _lib.check(_lib.lib().apr_select_dns(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1], _ptr(u_dns, torch.int32),
+                                         _ptr(j_dns, torch.int32), n_pos, dns, _ptr(out), _stream()))
+    return out
+
+
+class TrainWorkspace:
+    """Caller-owned scratch of apr_train_steps for up to (n_steps, batch, d)."""
+
+    def __init__(self, n_steps: int, batch: int, d: int, device):
+        nbytes = _lib.lib().apr_train_workspace_bytes(n_steps, batch, d)
+        if nbytes < 0:
+            raise ValueError("bad workspace shape (n_steps=%d, batch=%d, d=%d)" % (n_steps, batch, d))
+        self.n_steps, self.batch, self.d, self.nbytes = n_steps, batch, d, nbytes
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(_lib.lib().apr_train_workspace_init(self.buf.data_ptr(), nbytes, _stream()))
+
+    def fits(self, n_steps: int, batch: int, d: int) -> bool:
+        return batch == self.batch and d == self.d and n_steps <= self.n_steps
+
+    def unique_counts(self, n_steps: int) -> np.ndarray:
+        """[n_steps, 2] {unique users, unique items} of the last prepared chunk (synchronises).
+        Raises if an out-of-range id was seen."""
+        out = np.zeros((n_steps, 2), dtype=np.int32)
+        _lib.check(_lib.lib().apr_train_unique_counts(self.buf.data_ptr(), n_steps, self.batch, self.d,
+                                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _stream()))
+        return out
+
+
+def _train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws: TrainWorkspace, stats):
+    S, B = u.shape
+    d = P.shape[1]
+    if i.shape != u.shape or j.shape != u.shape:
+        raise ValueError("u, i, j must have the same [n_steps, batch] shape")
+    if not ws.fits(S, B, d):
+        raise ValueError("workspace was sized for (%d,%d,%d), got (%d,%d,%d)" % (ws.n_steps, ws.batch, ws.d, S, B, d))
+    if accP.shape != P.shape or accQ.shape != Q.shape:
+        raise ValueError("accumulator shape mismatch")
+    return (_ptr(P, torch.float32), _ptr(Q, torch.float32), _ptr(accP, torch.float32), _ptr(accQ, torch.float32),
+            P.shape[0], Q.shape[0], d, _ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), S, B, float(lr),
+            float(reg), float(reg_adv), float(eps), int(bool(adver)), int(mode), ws.buf.data_ptr(), ws.nbytes,
+            _ptr(stats, torch.float32), _stream())
+
+
+def train_steps(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: TrainWorkspace, mode: int = 0,
+                stats: Optional[torch.Tensor] = None) -> None:
+    """training_batch over u.shape[0] batches (utils.py:106-119), in place on P, Q, accP, accQ."""
+    _lib.check(_lib.lib().apr_train_steps(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
+
+
+def train_prepare(P, Q, u, i, j, ws: TrainWorkspace) -> None:
+    S, B = u.shape
+    _lib.check(_lib.lib().apr_train_prepare(_ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), S, B, P.shape[1],
+                                            P.shape[0], Q.shape[0], ws.buf.data_ptr(), ws.nbytes, _stream()))
+
+
+def train_run(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: TrainWorkspace, mode: int = 0,
+              stats: Optional[torch.Tensor] = None) -> None:
+    _lib.check(_lib.lib().apr_train_run(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
+
+
+def loss_acc(P, Q, u, i, j) -> torch.Tensor:
+    """-> float64 [S,2]: per batch {sum softplus(-r), count(x>0)} (utils.py:159-175)."""
+    S, B = u.shape
+    out = torch.empty((S, 2), dtype=torch.float64, device=P.device)
+    _lib.check(_lib.lib().apr_loss_acc(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1], _ptr(u, torch.int32),
+                                       _ptr(i, torch.int32), _ptr(j, torch.int32), S, B, _ptr(out), _stream()))
+    return out
+
+
+def score_pairs(P, Q, users, items) -> torch.Tensor:
+    n = users.numel()
+    out = torch.empty(n, dtype=torch.float32, device=P.device)
+    if n:
+        _lib.check(_lib.lib().apr_score_pairs(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1],
+                                              _ptr(users, torch.int32), _ptr(items, torch.int32), n, _ptr(out), _stream()))
+    return out
+
+
+def eval_candidates(P, Q, users, cand_ptr, cand_idx, want_scores: bool = False):
+    n = users.numel()
+    pos = torch.empty(n, dtype=torch.int32, device=P.device)
+    scores = torch.empty(cand_idx.numel(), dtype=torch.float32, device=P.device) if want_scores else None
+    _lib.check(_lib.lib().apr_eval_candidates(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1],
+                                              _ptr(users, torch.int32), _ptr(cand_ptr, torch.int64),
+                                              _ptr(cand_idx, torch.int32), n, _ptr(pos), _ptr(scores), _stream()))
+    return pos, scores
+
+
+def eval_fullrank(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, excl_idx, k_top: int = 0,
+                  exact: bool = False, position: Optional[torch.Tensor] = None):
+    """-> (position[int32 n], topk_ids[n,k] | None, topk_scores[n,k] | None)  (utils.py:210-215,244-261)."""
+    n = users.numel()
+    d = P.shape[1]
+    dev = P.device
+    if position is None:
+        position = torch.zeros(n, dtype=torch.int32, device=dev)
+    nbytes = _lib.lib().apr_eval_workspace_bytes(n, k_top, d)
+    if nbytes < 0:
+        raise ValueError("bad eval shape (n_users=%d, k_top=%d, d=%d); k_top must be <= 128" % (n, k_top, d))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    ids = torch.empty((n, k_top), dtype=torch.int32, device=dev) if k_top else None
+    sc = torch.empty((n, k_top), dtype=torch.float32, device=dev) if k_top else None
+    if excl_idx.numel() == 0:
+        excl_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().apr_eval_fullrank(_ptr(P, torch.float32), _ptr(Q, torch.float32), d, _ptr(users, torch.int32),
+                                            _ptr(test_item, torch.int32), n, item_lo, item_hi, _ptr(excl_ptr, torch.int64),
+                                            _ptr(excl_idx, torch.int32), k_top, _ptr(position, torch.int32), _ptr(ids),
+                                            _ptr(sc), int(bool(exact)), ws.data_ptr(), ws.numel(), _stream()))
+    return position, ids, sc
+
+
+def sum_squares(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().apr_sum_squares(_ptr(x, torch.float32), x.numel(), _ptr(out), _stream()))
+    return out

@@ -1,0 +1,8 @@
+"""Import alias for the package directory ``adversarial-collaborative-filtering_b200`` (not a valid identifier)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "adversarial-collaborative-filtering_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

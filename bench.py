@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- APR training throughput (triples/s) on BASELINE.json config 4 (synthetic 10M users x 2M items, d=128),
+plus full-rank evaluation users/s, with roofline / cpu_baseline / e2e objects (contract in the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--mode 0|1] [--impl reference]
+
+A "step" is one optimizer step = one batch of B triples through training_batch (utils.py:113-119): Delta update
++ Adagrad on L + reg_adv L_adv.  Tables (12.3 GB with Adagrad slots) are far larger than the 126 MB L2, so successive
+steps touch cold rows ("inputs larger than L2").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "apr_train_triples_per_s"
+UNIT = "triples/s"
+CFG = {"users": 10_000_000, "items": 2_000_000, "d": 128, "eps": 0.5, "reg_adv": 1.0, "lr": 0.05, "reg": 0.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4096)
+    ap.add_argument("--warmup", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("APR_BENCH_BATCH", "16384")))
+    ap.add_argument("--mode", type=int, default=int(os.environ.get("APR_BENCH_MODE", "1")))
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--users", type=int, default=CFG["users"])
+    ap.add_argument("--items", type=int, default=CFG["items"])
+    ap.add_argument("--dim", type=int, default=CFG["d"])
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_triples(rng, n_steps, batch, users, items):
+    u = rng.integers(0, users, size=(n_steps, batch), dtype=np.int32)
+    i = rng.integers(0, items, size=(n_steps, batch), dtype=np.int32)
+    j = rng.integers(0, items, size=(n_steps, batch), dtype=np.int32)
+    return u, i, j
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's step on touched rows only (same arithmetic as oracle.apr_step)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_sparse(O, P, Q, aP, aQ, u, i, j, lr, reg, reg_adv, eps, adver):
+    uu, inv_u = np.unique(u, return_inverse=True)
+    ii, inv = np.unique(np.concatenate([i, j]), return_inverse=True)
+    Pc, Qc, aPc, aQc = P[uu], Q[ii], aP[uu], aQ[ii]
+    O.apr_step(Pc, Qc, aPc, aQc, inv_u, inv[:i.size], inv[i.size:], lr, reg, reg_adv, eps, adver)
+    P[uu], Q[ii], aP[uu], aQ[ii] = Pc, Qc, aPc, aQc
+
+
+def cpu_baseline(args, seconds, n_steps_cap=None):
+    """Times the NumPy oracle (kind 'port': TensorFlow cannot run here) on the host cores, same shapes."""
+    from oracle import apr_oracle as O
+    rng = np.random.default_rng(2019)
+    U, I, d, B = args.users, args.items, args.dim, args.batch
+    # lazily-committed tables: only touched rows ever become resident
+    P, Q = np.zeros((U, d), np.float32), np.zeros((I, d), np.float32)
+    aP, aQ = np.zeros((U, d), np.float32), np.zeros((I, d), np.float32)
+    done, t_used, steps = 0, 0.0, 0
+    while t_used < seconds and (n_steps_cap is None or steps < n_steps_cap):
+        u, i, j = [x[0] for x in synth_triples(rng, 1, B, U, I)]
+        for T, A, idx in ((P, aP, np.unique(u)), (Q, aQ, np.unique(np.concatenate([i, j])))):
+            T[idx] = (rng.standard_normal((idx.size, d)) * 0.01).astype(np.float32)
+            A[idx] = 0.1
+        t0 = time.perf_counter()
+        cpu_step_sparse(O, P, Q, aP, aQ, u, i, j, CFG["lr"], CFG["reg"], CFG["reg_adv"], CFG["eps"], 1)
+        t_used += time.perf_counter() - t0
+        done += B
+        steps += 1
+    return done / t_used, steps, t_used
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = max(1, args.steps), max(0, args.warmup)
+    # each step = one batch through the oracle; bounded so that the run ends within minutes
+    K_run = min(K, 64)
+    if W:
+        cpu_baseline(args, 1e9, n_steps_cap=min(W, 2))
+    tps, steps, t = cpu_baseline(args, 1e9, n_steps_cap=K_run)
+    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d batches of %d triples, NumPy oracle (TensorFlow reference not installable: "
+                                       "no tensorflow/keras wheels in this image)" % (steps, args.batch)},
+            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host_cpus": os.cpu_count(), "timed_steps": steps}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "BASELINE.json configs[3]: synthetic %dM users x %dM items, d=%d, APR step (eps 0.5, reg_adv 1, "
+                        "lr 0.05, Adagrad), uniform triples" % (args.users // 10 ** 6, args.items // 10 ** 6, args.dim),
+            "users": args.users, "items": args.items, "d": args.dim, "batch_per_step": args.batch,
+            "step_mode": "persistent-cooperative" if args.mode == 1 else "kernel-per-phase",
+            "cache": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" %
+                     (2 * 4 * args.dim * (args.users + args.items) / 1e9)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from apr_b200 import engine
+    from apr_b200.APR import MF, Session
+    from apr_b200.utils import training_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = engine.require_cuda()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    U, I, d, B, K, W = args.users, args.items, args.dim, args.batch, max(1, args.steps), max(3, args.warmup)
+    hbm_peak, tc_peak, peak_kind = peaks()
+
+    # ---- model through the reference-facing surface -----------------------------------------------------
+    import types
+    margs = types.SimpleNamespace(embed_size=d, lr=CFG["lr"], reg=CFG["reg"], dns=1, adv="grad", eps=CFG["eps"], adver=1,
+                                  reg_adv=CFG["reg_adv"], epochs=0, seed=2019 + rank)
+    model = MF(U, I, margs)
+    model.extra_row = 0
+    model.build_graph()
+    sess = Session(mode=args.mode)
+    rng = np.random.default_rng(2019 + rank)
+
+    CH = max(1, min(256, (1 << 22) // B))  # steps per chunk (one prepare + one run each)
+
+    def device_chunk(n):
+        u, i, j = synth_triples(rng, n, B, U, I)
+        return [torch.from_numpy(x).to(dev) for x in (u, i, j)]
+
+    ws = sess.workspace(CH, B, d)
+    P, Q, aP, aQ = model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q
+    hp = (CFG["lr"], CFG["reg"], CFG["reg_adv"], CFG["eps"], 1)
+
+    def run_chunk(u, i, j):
+        engine.train_steps(P, Q, aP, aQ, u, i, j, *hp, ws, mode=args.mode)
+
+    # ---- warm-up ---------------------------------------------------------------------------------------
+    done = 0
+    while done < W:
+        n = min(CH, W - done)
+        run_chunk(*device_chunk(n))
+        done += n
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, ids resident in HBM -----------------------------------------------------
+    chunks = []
+    left = K
+    while left > 0:
+        n = min(CH, left)
+        chunks.append(device_chunk(n))
+        left -= n
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for c in chunks:
+        run_chunk(*c)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * K * B / (ms * 1e-3)
+    launches = sum(4 + (1 if args.mode == 1 else 3 * c[0].shape[0]) for c in chunks)
+
+    # ---- roofline of the dominant kernel(s): the embedding step kernels, index preparation excluded -------
+    # algorithmic bytes per step = 16 d (U_uniq + I_uniq) + 12 B   
+    n_roof = min(len(chunks), 4)
+    bytes_total, ms_run = 0.0, 0.0
+    for c in chunks[:n_roof]:
+        engine.train_prepare(P, Q, *c, ws)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engine.train_run(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_run += e0.elapsed_time(e1)
+        cnt = ws.unique_counts(c[0].shape[0]).astype(np.int64)
+        bytes_total += float(16 * d * cnt.sum() + 12 * B * c[0].shape[0])
+    achieved = bytes_total / (ms_run * 1e-3) / 1e9
+    steps_roof = sum(c[0].shape[0] for c in chunks[:n_roof])
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_kind": peak_kind,
+                "kernel": "step_persistent_kernel<32,1>" if args.mode == 1 else "step_phase_kernel<32,1,{1,2,3}>",
+                "bytes_per_step_model": bytes_total / steps_roof, "ms_per_step_kernel": ms_run / steps_roof}
+
+    # ---- e2e: public API with HOST batches; H2D of ids and D2H of the per-step loss inside the region ------
+    Ke = min(K, 4 * CH)
+    hu, hi, hj = synth_triples(rng, Ke, B, U, I)
+    stats = torch.zeros((Ke, 2), dtype=torch.float32, device=dev)
+
+    def e2e_pass():
+        from apr_b200.utils import as_device_batches
+        Ud, Id, Jd = [as_device_batches(x, dev) for x in (hu, hi, hj)]
+        sess.train_steps(model, Ud, Id, Jd, adver=True, stats=stats)
+        return stats.cpu()
+
+    e2e_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_pass()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = {"value": world * Ke * B / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8,
+           "steps": Ke, "api": "Session.train_steps(model, host batches) == utils.training_batch"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args), "roofline": roofline, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks}
+
+    # ---- second headline metric: full-rank evaluation users/s (BASELINE.json configs[2] shape) ------------
+    if not args.no_eval and rank == 0:
+        try:
+            line["eval"] = bench_eval(torch, engine, dev, tc_peak)
+        except Exception as e:  # never lose the training line
+            line["eval"] = {"error": repr(e)}
+
+    if rank == 0 and not args.no_cpu:
+        tps, steps, t = cpu_baseline(args, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d batches of %d triples in %.1f s, NumPy oracle on touched rows "
+                                          "(TensorFlow reference not installable here)" % (steps, B, t),
+                                "host_cpus": os.cpu_count(),
+                                "reference_logs": "APR phase 15-87 k triples/s on unknown CPU (BASELINE.md 1.2)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_eval(torch, engine, dev, tc_peak):
+    """Full-rank leave-one-out evaluation on the yelp-sort shape (25 677 users x 25 815 items, d=128)."""
+    from apr_b200.Dataset import build_sorted_csr
+    U, I, d = 25677, 25815, 128
+    g = torch.Generator(device=dev)
+    g.manual_seed(2019)
+    P = torch.randn((U, d), device=dev, generator=g) / d ** 0.5
+    Q = torch.randn((I + 1, d), device=dev, generator=g) / d ** 0.5
+    rng = np.random.default_rng(7)
+    test = rng.integers(0, I, U).astype(np.int32)
+    lens = rng.integers(5, 60, U)
+    ptr = np.zeros(U + 1, np.int64)
+    ptr[1:] = np.cumsum(lens)
+    idx = np.sort(rng.integers(0, I, int(ptr[-1])).astype(np.int32))
+    # rows must be sorted and unique: build per row from a sorted global draw
+    rows = [np.unique(np.append(rng.integers(0, I, lens[k]), test[k])).astype(np.int32) for k in range(U)]
+    ptr[1:] = np.cumsum([r.size for r in rows])
+    idx = np.concatenate(rows)
+    t = lambda a, dt: torch.from_numpy(a).to(device=dev, dtype=dt)
+    a = [P, Q, t(np.arange(U, dtype=np.int32), torch.int32), t(test, torch.int32), 0, I, t(ptr, torch.int64), t(idx, torch.int32)]
+    out = {}
+    for name, k_top in (("position_only", 0), ("with_top10", 10)):
+        engine.eval_fullrank(*a, k_top)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            pos, _, _ = engine.eval_fullrank(*a, k_top)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"users_per_s": U / (ms * 1e-3), "ms": ms, "fp32_tflops": 2.0 * U * I * d / (ms * 1e-3) / 1e12}
+    out["workload"] = "synthetic yelp-sort shape %d users x %d items d=%d, exact fp32 order-pinned scores" % (U, I, d)
+    out["hr10"] = float((pos < 10).float().mean().item())
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+/*
+ * apr_b200.h -- C ABI of the B200-native APR / BPR-MF hot path (libapr_b200.so).
+ *
+ * The reference (feay1234/Adversarial-Collaborative-Filtering) is pure Python on TensorFlow-1.x and has
+ * NO native boundary; its seam for this path is `sess.run(fetches, feed_dict)` on attributes of class MF
+ * (APR.py:85-202) called from utils.py:106-267.  Each entry point below replaces one such fetch group and
+ * cites it.  INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch tensors on the Python side) unless the
+ *     parameter name ends in `_host`; nothing is retained after the call returns;
+ *   - tables are row-major float32 [rows, d], d % 4 == 0, 4 <= d <= 512, base pointers 16-byte aligned;
+ *   - ids are int32; CSR row pointers are int64;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host synchronisation unless
+ *     stated; the only allocations are the caller-provided workspaces;
+ *   - return value: 0 = ok, otherwise an APR_E_* code (apr_status_string() describes it).  There is no CPU
+ *     fallback: without a CUDA device every compute entry point returns APR_E_CUDA.
+ */
+#ifndef APR_B200_H_
+#define APR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APR_ABI_VERSION 1
+
+enum {
+  APR_OK = 0,
+  APR_E_ARG = 1,       /* bad shape / null pointer / unsupported d */
+  APR_E_ALIGN = 2,     /* pointer not 16-byte aligned */
+  APR_E_WORKSPACE = 3, /* workspace too small */
+  APR_E_CUDA = 4,      /* CUDA runtime error (see apr_last_cuda_error) */
+  APR_E_UNSUPPORTED = 5
+};
+
+typedef void* apr_stream_t;
+
+int apr_abi_version(void);
+const char* apr_status_string(int status);
+const char* apr_last_cuda_error(void);
+/* sm count / compute capability of the current device. */
+int apr_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- A1 / K12: MF._create_variables, APR.py:105-119 (tf.truncated_normal(mean 0, stddev)) and the
+ *      `--adv random` noise of APR.py:172-177.  Philox4x32-10, counter (e_lo, e_hi, attempt, table_id),
+ *      key (seed, stream_tag); see oracle/apr_oracle.py:truncated_normal. */
+int apr_init_truncated_normal(float* W, int64_t rows, int32_t d, float stddev, uint32_t seed, uint32_t table_id,
+                              uint32_t stream_tag, apr_stream_t stream);
+int apr_fill_f32(float* x, int64_t n, float value, apr_stream_t stream);
+
+/* ---- A8 / K6: shuffle + _get_train_batch, APR.py:39-81.  Epoch permutation (Feistel bijection keyed by
+ *      (seed, epoch)) of the n_pairs (u,i) pairs, tail batch dropped, and `dns` uniform negatives per positive in
+ *      [0,num_items) rejected against the sorted CSR of trainList (csr_rows rows).  Outputs: out_u/out_i
+ *      [S*B], out_udns/out_j [S*B*dns] with S = n_pairs / batch.  *err_flag (device int32) is set non-zero if a
+ *      draw did not terminate within 65536 attempts.  Bit-exact with oracle.sample_epoch. */
+int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch, int32_t num_items,
+                     const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows, uint32_t seed, uint32_t epoch,
+                     int32_t dns, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
+                     apr_stream_t stream);
+
+/* ---- A7 (dns > 1 branch), utils.py:121-139: for each positive keep the best-scored of its dns negatives
+ *      (first maximum wins).  u_dns/j_dns are [n_pos*dns]; out_j is [n_pos]. */
+int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_dns, const int32_t* j_dns, int64_t n_pos,
+                   int32_t dns, int32_t* out_j, apr_stream_t stream);
+
+/* ---- A2-A7 / K1-K5: training_batch, utils.py:106-119: for every batch s of n_steps,
+ *        if adver: sess.run([update_P, update_Q])   (APR.py:180-191)   Delta = eps * G / ||G|| per touched row
+ *        sess.run(optimizer)                        (APR.py:143-165,193-195)  Adagrad on
+ *                                                   L + reg_adv * L_adv + reg-terms, duplicates summed.
+ *      u,i,j are [n_steps * batch].  accP/accQ are the Adagrad accumulators (same shape as P/Q, init 0.1).
+ *      Delta never exists as a table: it lives in a per-step workspace of touched rows.
+ *      The workspace must hold apr_train_workspace_bytes(n_steps, batch, d) bytes and must have been zeroed once
+ *      with apr_train_workspace_init before first use (the kernels restore the zero invariant themselves).
+ *      stats (nullable) receives per step {sum softplus(-r) of the PLAIN forward, count(x > 0)} as float[2].
+ *      mode: 0 = one kernel launch per phase (3 per APR step, 2 per BPR step);
+ *            1 = one persistent cooperative kernel for all n_steps (grid barriers between phases). */
+int64_t apr_train_workspace_bytes(int32_t n_steps, int32_t batch, int32_t d);
+int apr_train_workspace_init(void* workspace, int64_t workspace_bytes, apr_stream_t stream);
+int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
+                    const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, float lr,
+                    float reg, float reg_adv, float eps, int32_t adver, int32_t mode, void* workspace,
+                    int64_t workspace_bytes, float* stats, apr_stream_t stream);
+/* The two halves of apr_train_steps, exposed so the index preparation (hash de-duplication of the rows each batch
+ * touches) can be timed and profiled separately from the embedding kernels. */
+int apr_train_prepare(const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, int32_t d,
+                      int64_t rows_p, int64_t rows_q, void* workspace, int64_t workspace_bytes, apr_stream_t stream);
+int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
+                  const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, float lr,
+                  float reg, float reg_adv, float eps, int32_t adver, int32_t mode, void* workspace,
+                  int64_t workspace_bytes, float* stats, apr_stream_t stream);
+/* Per-step unique-row counts produced by apr_train_prepare (for the algorithmic-bytes model of the roofline):
+ * copies n_steps int32 pairs {unique users, unique items} to the HOST buffer; synchronises the stream.
+ * Returns APR_E_ARG if any id seen by apr_train_prepare since apr_train_workspace_init was outside its table
+ * (such ids are clamped to row 0 on the device instead of faulting). */
+int apr_train_unique_counts(const void* workspace, int32_t n_steps, int32_t batch, int32_t d, int32_t* counts_host,
+                            apr_stream_t stream);
+
+/* ---- A9 / K7: training_loss_acc, utils.py:159-175 (output_adv = 0): per batch s,
+ *      out[2s] = sum_b softplus(-clip(x_b)), out[2s+1] = count(x_b > 0), as float64. */
+int apr_loss_acc(const float* P, const float* Q, int32_t d, const int32_t* u, const int32_t* i, const int32_t* j,
+                 int32_t n_steps, int32_t batch, double* out, apr_stream_t stream);
+
+/* ---- A2 / Recommender.rank (MF.py:37-39, utils.py:246-251): scores[k] = <P[users[k]], Q[items[k]]> with the
+ *      pinned order acc = fmaf(p[t], q[t], acc), t ascending (oracle.score_pairs). */
+int apr_score_pairs(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* items, int64_t n,
+                    float* scores, apr_stream_t stream);
+
+/* ---- A10 / K8: _eval_by_user on explicit candidate lists, utils.py:244-254 and evaluation.py:114-128.
+ *      User k has candidates cand_idx[cand_ptr[k] .. cand_ptr[k+1]) with the held-out item LAST;
+ *      position[k] = #(score(neg) >= score(held-out)).  scores (nullable) receives every candidate score. */
+int apr_eval_candidates(const float* P, const float* Q, int32_t d, const int32_t* users, const int64_t* cand_ptr,
+                        const int32_t* cand_idx, int32_t n_users, int32_t* position, float* scores,
+                        apr_stream_t stream);
+
+/* ---- A10 / K9: _eval_by_user with eval_mode == "all", utils.py:210-215,244-261.  For each listed user:
+ *      candidates = [item_lo, item_hi) minus excl(u) (sorted CSR; = trainList[u] united with the held-out item),
+ *      position[k] += #(candidates c : score(u,c) >= score(u, test_item[k])), scores in the pinned fma order;
+ *      topk (nullable, k_top > 0): the k_top best candidates by (score desc, item id asc) of this item range,
+ *      topk_ids/topk_scores [n_users, k_top], padded with id -1 / -inf.  position must be zeroed by the caller
+ *      (item-sharded callers sum the shards' counts).  `exact` = 1 forces the fp32 CUDA-core kernel; 0 lets the
+ *      library use the tcgen05 bf16x3 filter + exact re-scoring (same results).
+ *      The workspace must hold apr_eval_workspace_bytes(n_users, k_top, d) bytes. */
+int64_t apr_eval_workspace_bytes(int32_t n_users, int32_t k_top, int32_t d);
+int apr_eval_fullrank(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                      int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                      const int32_t* excl_idx, int32_t k_top, int32_t* position, int32_t* topk_ids, float* topk_scores,
+                      int32_t exact, void* workspace, int64_t workspace_bytes, apr_stream_t stream);
+
+/* ---- K11: np.linalg.norm(embedding_P) of utils.py:92-97: *out (device double) = sum of squares. */
+int apr_sum_squares(const float* x, int64_t n, double* out, apr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APR_B200_H_ */

@@ -1,0 +1,283 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): sampled indices, rank positions and top-K ids bit-exact; losses, gradients and
+embeddings within 1e-5 relative in fp32.  "Relative" for a tensor means |a-b| <= RTOL * max|ref| element-wise
+(sums of signed terms cancel, so a per-element relative bound is not meaningful for fp32 atomics).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import apr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _close(got, ref, rtol=RTOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(got - ref).max()) / scale
+    assert err <= rtol, "max error %.3g of scale %.3g" % (err * scale, scale)
+
+
+def _dev(a, dtype, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+
+
+def _problem(rng, U, I, d, S, B, scale=0.1, zipf=False):
+    P = (rng.randn(U, d) * scale).astype(np.float32)
+    Q = (rng.randn(I, d) * scale).astype(np.float32)
+    if zipf:
+        w = 1.0 / np.arange(1, I + 1) ** 1.05
+        w /= w.sum()
+        i = rng.choice(I, size=(S, B), p=w)
+        j = rng.choice(I, size=(S, B), p=w)
+        wu = 1.0 / np.arange(1, U + 1)
+        u = rng.choice(U, size=(S, B), p=wu / wu.sum())
+    else:
+        u = rng.randint(0, U, (S, B))
+        i = rng.randint(0, I, (S, B))
+        j = rng.randint(0, I, (S, B))
+    return P, Q, u.astype(np.int32), i.astype(np.int32), j.astype(np.int32)
+
+
+def _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, adver):
+    P, Q = P.copy(), Q.copy()
+    aP = np.full_like(P, 0.1)
+    aQ = np.full_like(Q, 0.1)
+    stats = []
+    for s in range(u.shape[0]):
+        stats.append(O.loss_acc(P, Q, u[s], i[s], j[s]))
+        O.apr_step(P, Q, aP, aQ, u[s], i[s], j[s], lr, reg, reg_adv, eps, adver)
+    return P, Q, aP, aQ, np.asarray(stats)
+
+
+def _run_cuda_steps(dev, P, Q, u, i, j, lr, reg, reg_adv, eps, adver, mode):
+    from apr_b200 import engine
+    tP, tQ = _dev(P, torch.float32, dev), _dev(Q, torch.float32, dev)
+    aP, aQ = torch.full_like(tP, 0.1), torch.full_like(tQ, 0.1)
+    S, B = u.shape
+    ws = engine.TrainWorkspace(S, B, P.shape[1], dev)
+    stats = torch.zeros((S, 2), dtype=torch.float32, device=dev)
+    engine.train_steps(tP, tQ, aP, aQ, _dev(u, torch.int32, dev), _dev(i, torch.int32, dev), _dev(j, torch.int32, dev), lr,
+                       reg, reg_adv, eps, adver, ws, mode=mode, stats=stats)
+    torch.cuda.synchronize()
+    counts = ws.unique_counts(S)
+    # the workspace must be back to its all-zero invariant (G_Q / H_Q slots re-zeroed by phase 3)
+    nzero = 256 + 2 * (2 * B * P.shape[1] * 4)
+    assert int(ws.buf[256:nzero].count_nonzero().item()) == 0
+    return tP.cpu().numpy(), tQ.cpu().numpy(), aP.cpu().numpy(), aQ.cpu().numpy(), stats.cpu().numpy(), counts
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("adver", [0, 1])
+@pytest.mark.parametrize("d,U,I,S,B,zipf", [
+    (64, 300, 200, 6, 512, False),     # reference batch size, heavy duplication
+    (128, 5000, 3000, 3, 2048, False),
+    (8, 50, 40, 4, 96, False),         # lane groups of 4 with predication
+    (20, 64, 64, 3, 100, True),        # d not a power of two, Zipf users and items
+    (256, 700, 900, 2, 777, True),     # two float4 per lane
+    (384, 100, 100, 2, 130, False),
+    (512, 64, 80, 2, 64, False),
+])
+def test_train_steps_match_oracle(cuda_device, mode, adver, d, U, I, S, B, zipf):
+    rng = np.random.RandomState(d + B)
+    P, Q, u, i, j = _problem(rng, U, I, d, S, B, zipf=zipf)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 1.0, 0.5
+    rP, rQ, raP, raQ, rstats = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, adver)
+    gP, gQ, gaP, gaQ, gstats, counts = _run_cuda_steps(cuda_device, P, Q, u, i, j, lr, reg, reg_adv, eps, adver, mode)
+    _close(gP, rP)
+    _close(gQ, rQ)
+    _close(gaP, raP)
+    _close(gaQ, raQ)
+    _close(gstats[:, 0], rstats[:, 0])
+    assert np.array_equal(gstats[:, 1].astype(np.int64), rstats[:, 1].astype(np.int64))
+    for s in range(S):  # exact unique-row counts feed the roofline byte model
+        assert counts[s, 0] == np.unique(u[s]).size
+        assert counts[s, 1] == np.unique(np.concatenate([i[s], j[s]])).size
+
+
+def test_train_step_single_triple_and_self_pair(cuda_device):
+    # B = 1, and a triple whose positive and negative item coincide (x = 0, gradients cancel on the item row)
+    rng = np.random.RandomState(5)
+    P, Q, u, i, j = _problem(rng, 4, 4, 16, 2, 1)
+    j[1] = i[1]
+    for adver in (0, 1):
+        rP, rQ, raP, raQ, _ = _run_oracle_steps(P, Q, u, i, j, 0.05, 0.0, 1.0, 0.5, adver)
+        gP, gQ, gaP, gaQ, _, _ = _run_cuda_steps(cuda_device, P, Q, u, i, j, 0.05, 0.0, 1.0, 0.5, adver, 0)
+        _close(gP, rP)
+        _close(gQ, rQ)
+        _close(gaQ, raQ)
+
+
+def test_train_rejects_bad_arguments(cuda_device):
+    from apr_b200 import _lib, engine
+    dev = cuda_device
+    P = torch.zeros((10, 8), device=dev)
+    Q = torch.zeros((10, 8), device=dev)
+    u = torch.zeros((1, 4), dtype=torch.int32, device=dev)
+    ws = engine.TrainWorkspace(1, 4, 8, dev)
+    with pytest.raises(ValueError):
+        engine.train_steps(P, Q, P.clone(), Q.clone(), u, u, u[:, :2], 0.05, 0, 1, 0.5, 1, ws)
+    with pytest.raises(ValueError):  # d not a multiple of 4
+        engine.TrainWorkspace(1, 4, 6, dev)
+    bad = torch.full((1, 4), 10, dtype=torch.int32, device=dev)  # id == rows -> flagged, not a fault
+    engine.train_steps(P, Q, torch.full_like(P, 0.1), torch.full_like(Q, 0.1), bad, u, u, 0.05, 0, 1, 0.5, 1, ws)
+    with pytest.raises(_lib.AprError):
+        ws.unique_counts(1)
+
+
+def test_loss_acc_matches_oracle(cuda_device):
+    from apr_b200 import engine
+    rng = np.random.RandomState(11)
+    for d in (64, 128, 24):
+        P, Q, u, i, j = _problem(rng, 400, 300, d, 5, 700, scale=0.8)
+        out = engine.loss_acc(_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+                              _dev(u, torch.int32, cuda_device), _dev(i, torch.int32, cuda_device),
+                              _dev(j, torch.int32, cuda_device)).cpu().numpy()
+        for s in range(5):
+            l, c = O.loss_acc(P, Q, u[s], i[s], j[s])
+            assert abs(out[s, 0] - l) <= RTOL * abs(l)
+            # x > 0 can flip only where |x| is at rounding level
+            x, _, _ = O.forward(P, Q, u[s], i[s], j[s])
+            assert abs(int(out[s, 1]) - c) <= int((np.abs(x) < 1e-6).sum())
+
+
+def test_sampler_bit_exact(cuda_device):
+    from apr_b200 import engine
+    rng = np.random.RandomState(2)
+    U, I = 700, 450
+    lists = [sorted(set(rng.randint(0, I, rng.randint(1, 60)).tolist())) for _ in range(U)]
+    lists[3] = list(range(I - 1))  # a user with a single admissible negative
+    pu = np.concatenate([[u] * len(l) for u, l in enumerate(lists)]).astype(np.int32)
+    pi = np.concatenate(lists).astype(np.int32)
+    ptr, idx = O.build_csr(lists[:-5])  # trainList shorter than num_users: the tail users reject nothing
+    for B, dns, epoch in ((512, 1, 0), (100, 3, 7), (1, 1, 2)):
+        want = O.sample_epoch(pu, pi, B, I, ptr, idx, 2019, epoch, dns)
+        got = engine.sample_epoch(_dev(pu, torch.int32, cuda_device), _dev(pi, torch.int32, cuda_device), B, I,
+                                  _dev(ptr, torch.int64, cuda_device), _dev(idx, torch.int32, cuda_device), 2019, epoch, dns)
+        assert int(got[4].item()) == 0
+        for g, w in zip(got[:4], want):
+            assert np.array_equal(g.cpu().numpy(), w)
+
+
+def test_select_dns_bit_exact(cuda_device):
+    from apr_b200 import engine
+    rng = np.random.RandomState(4)
+    P, Q, _, _, _ = _problem(rng, 100, 90, 64, 1, 1, scale=1.0)
+    ud = np.repeat(rng.randint(0, 100, 500), 4).astype(np.int32)
+    jd = rng.randint(0, 90, 2000).astype(np.int32)
+    jd[4:8] = jd[4]  # all-equal scores: first wins
+    got = engine.select_dns(_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+                            _dev(ud, torch.int32, cuda_device), _dev(jd, torch.int32, cuda_device), 4).cpu().numpy()
+    assert np.array_equal(got, O.select_dns(P, Q, ud, jd, 4))
+
+
+def test_truncated_normal_matches_oracle(cuda_device):
+    from apr_b200 import engine
+    W = torch.empty((1000, 64), dtype=torch.float32, device=cuda_device)
+    engine.init_truncated_normal(W, 0.01, 2019, 1)
+    ref = O.truncated_normal(1000, 64, 0.01, 2019, 1)
+    got = W.cpu().numpy()
+    # transcendental functions differ in the last ulp between libm and CUDA: tolerance, not bit-exactness
+    assert np.abs(got - ref).max() <= 1e-5 * 0.02
+    assert np.abs(got).max() <= 0.02
+
+
+@pytest.mark.parametrize("d", [8, 64, 100, 128, 256])
+def test_scores_bit_exact(cuda_device, d):
+    from apr_b200 import engine
+    rng = np.random.RandomState(d)
+    P, Q, _, _, _ = _problem(rng, 200, 300, d, 1, 1, scale=1.0)
+    us = rng.randint(0, 200, 5000).astype(np.int32)
+    it = rng.randint(0, 300, 5000).astype(np.int32)
+    got = engine.score_pairs(_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+                             _dev(us, torch.int32, cuda_device), _dev(it, torch.int32, cuda_device)).cpu().numpy()
+    want = O.score_pairs(P, Q, us, it)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_eval_candidates_bit_exact(cuda_device):
+    from apr_b200 import engine
+    rng = np.random.RandomState(9)
+    P, Q, _, _, _ = _problem(rng, 120, 500, 64, 1, 1, scale=1.0)
+    Q[17] = Q[400]  # exact ties, including with held-out items
+    users = np.arange(120, dtype=np.int32)
+    rows, ptr = [], [0]
+    for u in users:
+        n = [0, 1, 100, 101, 257][u % 5]
+        c = rng.randint(0, 500, n).tolist() + [17 if u % 3 == 0 else int(rng.randint(0, 500))]
+        if n:
+            c[0] = 400
+        rows.append(c)
+        ptr.append(ptr[-1] + len(c))
+    cand = np.concatenate(rows).astype(np.int32)
+    pos, sc = engine.eval_candidates(_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+                                     _dev(users, torch.int32, cuda_device), _dev(np.asarray(ptr), torch.int64, cuda_device),
+                                     _dev(cand, torch.int32, cuda_device), want_scores=True)
+    pos = pos.cpu().numpy()
+    for u in users:
+        assert pos[u] == O.eval_candidates_position(P, Q, int(u), rows[u])
+    want = O.score_pairs(P, Q, np.repeat(users, np.diff(ptr)), cand)
+    assert np.array_equal(sc.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def _fullrank_case(rng, U, I, d, rows_extra=1, scale=1.0, ties=True):
+    P = (rng.randn(U + rows_extra, d) * scale).astype(np.float32)
+    Q = (rng.randn(I + rows_extra, d) * scale).astype(np.float32)
+    if ties:
+        Q[I // 2] = Q[1]
+        Q[I // 3] = Q[1]
+    train = [sorted(set(rng.randint(0, I, rng.randint(0, 30)).tolist())) for _ in range(U)]
+    test = rng.randint(0, I + rows_extra, U).astype(np.int32)  # may be == num_items (Video: test id 23714)
+    test[0] = 1
+    test[1] = I // 2
+    if train[2]:
+        test[2] = train[2][0]  # held-out item that is also a train item
+    return P, Q, train, test
+
+
+@pytest.mark.parametrize("U,I,d,k_top", [(150, 333, 64, 0), (150, 333, 64, 10), (70, 1000, 128, 100), (33, 2100, 32, 128),
+                                         (64, 64, 256, 5), (200, 130, 20, 100)])
+def test_eval_fullrank_bit_exact(cuda_device, U, I, d, k_top):
+    from apr_b200 import engine
+    from apr_b200.Dataset import build_sorted_csr
+    rng = np.random.RandomState(U + I)
+    P, Q, train, test = _fullrank_case(rng, U, I, d)
+    ptr, idx = build_sorted_csr([train[u] + [int(test[u])] for u in range(U)])
+    users = np.arange(U, dtype=np.int32)
+    pos, ids, sc = engine.eval_fullrank(_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+                                        _dev(users, torch.int32, cuda_device), _dev(test, torch.int32, cuda_device), 0, I,
+                                        _dev(ptr, torch.int64, cuda_device), _dev(idx, torch.int32, cuda_device), k_top,
+                                        exact=True)
+    pos = pos.cpu().numpy()
+    ids = ids.cpu().numpy() if k_top else None
+    for u in range(U):
+        p, nneg, tids, tsc = O.eval_fullrank_user(P, Q, u, int(test[u]), train[u], I, max(k_top, 1))
+        assert pos[u] == p, (u, pos[u], p)
+        if k_top:
+            # library returns the top-k of the NEGATIVES; the held-out item enters at rank `position` (loses ties)
+            neg_ids = [t for t in ids[u].tolist() if t >= 0]
+            merged = neg_ids[:p] + [int(test[u])] + neg_ids[p:] if p < k_top else neg_ids
+            assert merged[:k_top] == tids.tolist()[:k_top], u
+
+
+def test_eval_fullrank_item_sharded_sums(cuda_device):
+    """Item-sharded evaluation: per-shard counts add up to the single-range count."""
+    from apr_b200 import engine
+    from apr_b200.Dataset import build_sorted_csr
+    rng = np.random.RandomState(77)
+    U, I, d = 90, 1500, 64
+    P, Q, train, test = _fullrank_case(rng, U, I, d)
+    ptr, idx = build_sorted_csr([train[u] + [int(test[u])] for u in range(U)])
+    a = [_dev(P, torch.float32, cuda_device), _dev(Q, torch.float32, cuda_device),
+         _dev(np.arange(U, dtype=np.int32), torch.int32, cuda_device), _dev(test, torch.int32, cuda_device)]
+    e = [_dev(ptr, torch.int64, cuda_device), _dev(idx, torch.int32, cuda_device)]
+    whole, _, _ = engine.eval_fullrank(*a, 0, I, *e, 0, exact=True)
+    acc = torch.zeros(U, dtype=torch.int32, device=cuda_device)
+    for lo, hi in ((0, 401), (401, 1000), (1000, I)):
+        engine.eval_fullrank(*a, lo, hi, *e, 0, exact=True, position=acc)
+    assert torch.equal(whole, acc)
