@@ -6,22 +6,30 @@
 //     sess.run(optimizer)              APR.py:143-165,193-195   Adagrad on L(Theta) + reg_adv L(Theta+Delta) + reg
 //
 // Design (DESIGN.md "Training step"):
-//   prepare   hash de-duplication of the rows a batch touches.  Users: every distinct user of the batch becomes a
-//             SEGMENT (its triples made contiguous by a counting sort) owned by one lane group, so user-side sums
-//             (G_P, g_P) live in registers and the user's Adagrad update needs no atomics and no extra pass.
-//             Items: every distinct item gets a compact SLOT in an L2-resident workspace [<=2B, d].
-//   phase 1   per segment: gather p, per triple gather q,n (128-bit loads), x, c=-sigma(-x); G_P in registers;
-//             G_Q[slot] += +-c p by 16-byte vector RED at L2; c kept per triple.
-//   phase 2   per segment: Delta_P from G_P (group shuffle norm); per triple Delta_Q from G_Q[slot] rows, adversarial
-//             forward, c'; g_P in registers -> Adagrad on the user row; H_Q[slot] += total item gradient (RED).
-//   phase 3   per item slot: Adagrad on the item row with H_Q[slot]; G_Q, H_Q slots re-zeroed.
-//   Delta and per-triple gradients never exist in HBM as tables; only the touched-row workspace (L2 resident for
-//   B <= ~32k at d=128) is written.  BPR (adver=0) fuses phase 1+2.
-//   mode 0 launches one kernel per phase; mode 1 runs all steps in ONE persistent cooperative kernel with grid
-//   barriers between phases.
+//   prepare   hash de-duplication of the rows a batch touches, for all steps of a chunk at once.
+//             Users: every distinct user of a batch becomes a SEGMENT (its triples made contiguous by a counting
+//             sort) owned by one lane group, so user-side sums (G_P, g_P) live in registers.
+//             Items: an item that occurs ONCE in the batch is a singleton -- its row sums are local to its triple.
+//             Only SHARED items (>= 2 occurrences) get a slot in the L2-resident workspace G_Q / H_Q [<= B, d].
+//             Segments are PARTITIONED: slow ones (touching a shared item) first, fast ones after.
+//   FAST segment (no shared item; ~94% at B=65536 on 10M x 2M): the whole APR step in registers -- gather p, q, n
+//             and the three Adagrad rows with 128-bit loads, x, c = -sigma(-x), Delta from the local gradients,
+//             adversarial forward, total gradient, Adagrad, six row stores.  HBM traffic is exactly the algorithmic
+//             4 row-transfers per touched row; nothing else is written.
+//   SLOW segments, three stages separated by grid-wide ordering:
+//     stage 0  plain forward: G_P kept, c kept per triple, G_Q[slot] += +-c p by 16-byte vector RED at L2.
+//     stage 1  Delta_P from G_P, Delta_Q from G_Q[slot] (shared) or c p (singleton), adversarial forward; user row and
+//              singleton item rows get Adagrad directly; H_Q[slot] += g (RED).   + first half of the fast segments
+//     stage 2  per shared slot: Adagrad on the item row from H_Q[slot]; slots re-zeroed.  + second half of the fast ones
+//   so the slow path's dependent-load chains run under the fast bulk.  BPR (adver=0) has no stage 0.
+//   Delta and per-triple gradients never exist in HBM as tables.
+//   mode 0 launches one kernel per stage; mode 1 runs all steps in ONE persistent cooperative kernel with grid
+//   barriers between stages (one barrier per step when the batch has no shared item).
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -38,40 +46,48 @@ static inline int pow2ceil(int x) {
 // ------------------------------------------------------------------------------------------------
 // workspace layout
 // ------------------------------------------------------------------------------------------------
+// Index preparation runs in sub-chunks of `Sc` steps so that its hash tables stay L2-resident (<= ~48 MB).
 struct TrainLayout {
-  int S, B, d, Tu, Ti;
-  int64_t off_hdr, off_GQ, off_HQ, off_GP, off_cbuf, off_ucnt, off_icnt, off_useg_user, off_useg_off, off_ucursor,
-      off_uentry, off_strip, off_slot_i, off_slot_j, off_iu_item, off_tkey_u, off_tval_u, off_tkey_i, off_tval_i, total;
-  int64_t zero_bytes;  // [0, zero_bytes) must be zero between steps (hdr, GQ, HQ)
+  int S, B, d, Tu, Ti, Sc;
+  int64_t off_hdr, off_GQ, off_HQ, off_GP, off_cbuf, off_ucnt, off_icnt, off_iall, off_nslow, off_nfast, off_tcursor,
+      off_seg_slow, off_seg_user, off_seg_off, off_seg_cnt, off_ucursor, off_entry, off_rec, off_seg_hdr, off_iu_item, off_tkey_u, off_tval_u,
+      off_tkey_i, off_tval_i, total;
 };
 
 static TrainLayout make_layout(int S, int B, int d) {
   TrainLayout L;
   L.S = S; L.B = B; L.d = d;
-  L.Tu = max(32, 2 * pow2ceil(B));
-  L.Ti = max(32, 4 * pow2ceil(B));
+  L.Tu = std::max(32, 2 * pow2ceil(B));
+  L.Ti = std::max(32, 4 * pow2ceil(B));
+  const int64_t table_bytes_per_step = int64_t(L.Tu + L.Ti) * 8;
+  L.Sc = int(std::max<int64_t>(1, std::min<int64_t>(S, (int64_t(48) << 20) / table_bytes_per_step)));
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o += (bytes + 255) & ~int64_t(255); return r; };
-  L.off_hdr = take(256);
-  L.off_GQ = take(int64_t(2) * B * d * 4);
-  L.off_HQ = take(int64_t(2) * B * d * 4);
-  L.zero_bytes = o;
+  L.off_hdr = take(256);                       // word 0: id-out-of-range flag
+  L.off_GQ = take(int64_t(B) * d * 4);         // zero between steps
+  L.off_HQ = take(int64_t(B) * d * 4);         // zero between steps
   L.off_GP = take(int64_t(B) * d * 4);
   L.off_cbuf = take(int64_t(B) * 4);
-  L.off_ucnt = take(int64_t(S) * 4);
+  L.off_ucnt = take(int64_t(S) * 4);           // ucnt .. seg_slow are cleared together by prepare
   L.off_icnt = take(int64_t(S) * 4);
-  L.off_useg_user = take(int64_t(S) * B * 4);
-  L.off_useg_off = take(int64_t(S) * (B + 1) * 4);
+  L.off_iall = take(int64_t(S) * 4);
+  L.off_nslow = take(int64_t(S) * 4);
+  L.off_nfast = take(int64_t(S) * 4);
+  L.off_tcursor = take(int64_t(S) * 4);
+  L.off_seg_slow = take(int64_t(S) * B * 4);
+  L.off_seg_user = take(int64_t(S) * B * 4);
+  L.off_seg_off = take(int64_t(S) * B * 4);
+  L.off_seg_cnt = take(int64_t(S) * B * 4);
   L.off_ucursor = take(int64_t(S) * B * 4);
-  L.off_uentry = take(int64_t(S) * B * 4);
-  L.off_strip = take(int64_t(S) * B * 4);
-  L.off_slot_i = take(int64_t(S) * B * 4);
-  L.off_slot_j = take(int64_t(S) * B * 4);
-  L.off_iu_item = take(int64_t(S) * 2 * B * 4);
-  L.off_tkey_u = take(int64_t(S) * L.Tu * 4);
-  L.off_tval_u = take(int64_t(S) * L.Tu * 4);
-  L.off_tkey_i = take(int64_t(S) * L.Ti * 4);
-  L.off_tval_i = take(int64_t(S) * L.Ti * 4);
+  L.off_entry = take(int64_t(S) * B * 12);     // hash entries of (u, i, j) per triple
+  L.off_rec = take(int64_t(S) * B * 16);       // {i, j, slot_i, slot_j} in segment order
+  L.off_seg_hdr = take(int64_t(S) * B * 32);   // per segment {user, b0, count, slow} + its first triple's record,
+                                               // partitioned: slow segments first, then fast ones
+  L.off_iu_item = take(int64_t(S) * B * 4);    // shared slot -> item id
+  L.off_tkey_u = take(int64_t(L.Sc) * L.Tu * 4);
+  L.off_tval_u = take(int64_t(L.Sc) * L.Tu * 4);
+  L.off_tkey_i = take(int64_t(L.Sc) * L.Ti * 4);
+  L.off_tval_i = take(int64_t(L.Sc) * L.Ti * 4);
   L.total = o;
   return L;
 }
@@ -79,127 +95,165 @@ static TrainLayout make_layout(int S, int B, int d) {
 template <typename T>
 static inline T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
-// header word 0: id-out-of-range flag
 // ------------------------------------------------------------------------------------------------
-// prepare kernels
+// prepare kernels (all steps of a sub-chunk in parallel; one hash table per step).  `s0` = first step of the
+// sub-chunk: per-step arrays are indexed by the absolute step, tables by the step within the sub-chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void prep_insert_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i,
-                                   const int32_t* __restrict__ j, int S, int B, int64_t rows_p, int64_t rows_q, int Tu,
-                                   int Ti, int32_t* tkey_u, int32_t* tval_u, int32_t* tkey_i, int32_t* uentry,
-                                   int32_t* slot_i, int32_t* slot_j, int32_t* hdr) {
-  const int64_t total = int64_t(S) * 3 * B;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int s = int(t / (3 * int64_t(B)));
-    const int n = int(t - int64_t(s) * 3 * B);
-    const int which = n / B, b = n - which * B;
-    int32_t key;
-    int32_t* table;
-    int T;
-    int64_t rows;
-    if (which == 0) { key = u[int64_t(s) * B + b]; table = tkey_u + int64_t(s) * Tu; T = Tu; rows = rows_p; }
-    else if (which == 1) { key = i[int64_t(s) * B + b]; table = tkey_i + int64_t(s) * Ti; T = Ti; rows = rows_q; }
-    else { key = j[int64_t(s) * B + b]; table = tkey_i + int64_t(s) * Ti; T = Ti; rows = rows_q; }
-    if (key < 0 || key >= rows) { atomicOr(hdr, 1); key = 0; }
-    uint32_t h = fmix32(uint32_t(key)) & uint32_t(T - 1);
-    while (true) {
-      const int32_t prev = atomicCAS(&table[h], -1, key);
-      if (prev == -1 || prev == key) break;
-      h = (h + 1) & uint32_t(T - 1);
-    }
-    if (which == 0) { atomicAdd(&tval_u[int64_t(s) * Tu + h], 1); uentry[int64_t(s) * B + b] = int32_t(h); }
-    else if (which == 1) slot_i[int64_t(s) * B + b] = int32_t(h);
-    else slot_j[int64_t(s) * B + b] = int32_t(h);
+__device__ __forceinline__ uint32_t hash_insert(int32_t* table, int T, int32_t key, bool& dup) {
+  uint32_t h = fmix32(uint32_t(key)) & uint32_t(T - 1);
+  while (true) {
+    const int32_t prev = atomicCAS(&table[h], -1, key);
+    if (prev == -1) { dup = false; return h; }
+    if (prev == key) { dup = true; return h; }
+    h = (h + 1) & uint32_t(T - 1);
   }
 }
 
-// one thread per hash-table entry; warps never straddle tables (Tu, Ti are multiples of 32)
-__global__ void prep_compact_kernel(int S, int B, int Tu, int Ti, const int32_t* __restrict__ tkey_u, int32_t* tval_u,
-                                    const int32_t* __restrict__ tkey_i, int32_t* tval_i, int32_t* ucnt, int32_t* icnt,
-                                    int32_t* useg_user, int32_t* ucursor, int32_t* iu_item) {
-  const int64_t nU = int64_t(S) * Tu, nI = int64_t(S) * Ti;
+// one CAS per id; only duplicates pay a second atomic (users: extra count) or a flag store (items: "shared")
+__global__ void prep_insert_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                                   const int32_t* __restrict__ j, int s0, int ns, int B, int64_t rows_p, int64_t rows_q,
+                                   int Tu, int Ti, int32_t* tkey_u, int32_t* tval_u, int32_t* tkey_i, int32_t* tval_i,
+                                   int32_t* entry, int32_t* hdr) {
+  const int64_t total = int64_t(ns) * B;
+  for (int64_t tl = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; tl < total; tl += int64_t(gridDim.x) * blockDim.x) {
+    const int sl = int(tl / B);
+    const int64_t t = int64_t(s0) * B + tl;
+    int32_t ku = u[t], ki = i[t], kj = j[t];
+    if (ku < 0 || ku >= rows_p) { atomicOr(hdr, 1); ku = 0; }
+    if (ki < 0 || ki >= rows_q) { atomicOr(hdr, 1); ki = 0; }
+    if (kj < 0 || kj >= rows_q) { atomicOr(hdr, 1); kj = 0; }
+    bool dup;
+    const uint32_t hu = hash_insert(tkey_u + int64_t(sl) * Tu, Tu, ku, dup);
+    if (dup) atomicAdd(&tval_u[int64_t(sl) * Tu + hu], 1);
+    const uint32_t hi = hash_insert(tkey_i + int64_t(sl) * Ti, Ti, ki, dup);
+    if (dup) tval_i[int64_t(sl) * Ti + hi] = 1;
+    const uint32_t hj = hash_insert(tkey_i + int64_t(sl) * Ti, Ti, kj, dup);
+    if (dup) tval_i[int64_t(sl) * Ti + hj] = 1;
+    entry[3 * t] = int32_t(hu); entry[3 * t + 1] = int32_t(hi); entry[3 * t + 2] = int32_t(hj);
+  }
+}
+
+// one thread per hash-table entry; warps never straddle tables (Tu, Ti are multiples of 32).
+// users: every entry -> segment id + a range [b0, b0+count) of the step's triple slots (one atomic per warp on the
+// step's cursor; segment order is irrelevant).  items: flagged entries -> shared slot, others -> -1 (singleton).
+__global__ void prep_compact_kernel(int s0, int ns, int B, int Tu, int Ti, const int32_t* __restrict__ tkey_u,
+                                    int32_t* tval_u, const int32_t* __restrict__ tkey_i, int32_t* tval_i, int32_t* ucnt,
+                                    int32_t* icnt, int32_t* iall, int32_t* tcursor, int32_t* seg_user, int32_t* seg_off,
+                                    int32_t* seg_cnt, int32_t* ucursor, int32_t* iu_item) {
+  const int64_t nU = int64_t(ns) * Tu, nI = int64_t(ns) * Ti;
   const unsigned lane = threadIdx.x & 31;
   for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) & ~int64_t(31); base < nU + nI;
        base += int64_t(gridDim.x) * blockDim.x) {
     const int64_t e = base + lane;
     const bool is_user = e < nU;
-    int32_t key = -1;
+    int32_t key = -1, val = 0;
     int s = 0;
     int64_t ei = 0;
-    if (is_user) { s = int(e / Tu); key = tkey_u[e]; }
-    else { ei = e - nU; s = int(ei / Ti); key = tkey_i[ei]; }
+    if (is_user) { s = s0 + int(e / Tu); key = tkey_u[e]; if (key != -1) val = tval_u[e]; }
+    else { ei = e - nU; s = s0 + int(ei / Ti); key = tkey_i[ei]; if (key != -1) val = tval_i[ei]; }
     const bool valid = key != -1;
-    const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (m == 0) continue;
-    int basev = 0;
-    const int leader = __ffs(m) - 1;
-    if (int(lane) == leader) basev = atomicAdd(is_user ? &ucnt[s] : &icnt[s], __popc(m));
+    const bool slotted = valid && (is_user || val != 0);
+    const unsigned mv = __ballot_sync(0xffffffffu, valid);
+    const unsigned ms = __ballot_sync(0xffffffffu, slotted);
+    if (mv == 0) continue;
+    // inclusive warp scan of the user segment sizes
+    const int cnt = (is_user && valid) ? 1 + val : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (int(lane) >= o) incl += y;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    int basev = 0, baseo = 0;
+    const int leader = __ffs(mv) - 1;
+    if (int(lane) == leader) {
+      if (is_user) { basev = atomicAdd(&ucnt[s], __popc(ms)); baseo = atomicAdd(&tcursor[s], warp_total); }
+      else { atomicAdd(&iall[s], __popc(mv)); if (ms) basev = atomicAdd(&icnt[s], __popc(ms)); }
+    }
     basev = __shfl_sync(0xffffffffu, basev, leader);
+    baseo = __shfl_sync(0xffffffffu, baseo, leader);
     if (valid) {
-      const int slot = basev + __popc(m & ((1u << lane) - 1u));
+      const int slot = slotted ? basev + __popc(ms & ((1u << lane) - 1u)) : -1;
       if (is_user) {
-        useg_user[int64_t(s) * B + slot] = key;
-        ucursor[int64_t(s) * B + slot] = tval_u[e];
+        const int64_t k = int64_t(s) * B + slot;
+        seg_user[k] = key;
+        seg_off[k] = baseo + incl - cnt;
+        seg_cnt[k] = cnt;
+        ucursor[k] = 0;
         tval_u[e] = slot;
       } else {
-        iu_item[int64_t(s) * 2 * B + slot] = key;
+        if (slot >= 0) iu_item[int64_t(s) * B + slot] = key;
         tval_i[ei] = slot;
       }
     }
   }
 }
 
-// one CTA per step: exclusive scan of the per-segment counts -> segment offsets; counts reset to 0 (cursors)
-__global__ void __launch_bounds__(256) prep_scan_kernel(int B, const int32_t* __restrict__ ucnt, int32_t* ucursor,
-                                                        int32_t* useg_off) {
-  const int s = blockIdx.x;
-  const int nu = ucnt[s];
-  int32_t* cnt = ucursor + int64_t(s) * B;
-  int32_t* off = useg_off + int64_t(s) * (B + 1);
-  __shared__ int warp_tot[8];
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int base = 0; base < nu; base += 256) {
-    const int idx = base + threadIdx.x;
-    const int v = idx < nu ? cnt[idx] : 0;
-    int x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_tot[w] = x;
-    __syncthreads();
-    int wbase = 0;
-    for (int k = 0; k < w; ++k) wbase += warp_tot[k];
-    const int carry = carry_s;
-    if (idx < nu) { off[idx] = carry + wbase + x - v; cnt[idx] = 0; }
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + wbase + x;
-    __syncthreads();
+__global__ void prep_scatter_kernel(const int32_t* __restrict__ i, const int32_t* __restrict__ j, int s0, int ns, int B,
+                                    int Tu, int Ti, const int32_t* __restrict__ tval_u, const int32_t* __restrict__ tval_i,
+                                    const int32_t* __restrict__ entry, const int32_t* __restrict__ seg_off,
+                                    int32_t* ucursor, int4* rec, int32_t* seg_slow) {
+  const int64_t total = int64_t(ns) * B;
+  for (int64_t tl = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; tl < total; tl += int64_t(gridDim.x) * blockDim.x) {
+    const int sl = int(tl / B);
+    const int s = s0 + sl;
+    const int64_t t = int64_t(s0) * B + tl;
+    const int useg = tval_u[int64_t(sl) * Tu + entry[3 * t]];
+    const int si = tval_i[int64_t(sl) * Ti + entry[3 * t + 1]];
+    const int sj = tval_i[int64_t(sl) * Ti + entry[3 * t + 2]];
+    const int pos = seg_off[int64_t(s) * B + useg] + atomicAdd(&ucursor[int64_t(s) * B + useg], 1);
+    rec[int64_t(s) * B + pos] = make_int4(i[t], j[t], si, sj);
+    if (si >= 0 || sj >= 0) seg_slow[int64_t(s) * B + useg] = 1;
   }
-  if (threadIdx.x == 0) off[nu] = carry_s;
 }
 
-__global__ void prep_scatter_kernel(int S, int B, int Tu, int Ti, const int32_t* __restrict__ tval_u,
-                                    const int32_t* __restrict__ tval_i, const int32_t* __restrict__ uentry,
-                                    const int32_t* __restrict__ useg_off, int32_t* ucursor, int32_t* strip,
-                                    int32_t* slot_i, int32_t* slot_j) {
-  const int64_t total = int64_t(S) * 3 * B;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int s = int(t / (3 * int64_t(B)));
-    const int n = int(t - int64_t(s) * 3 * B);
-    const int which = n / B, b = n - which * B;
-    const int64_t sb = int64_t(s) * B + b;
-    if (which == 0) {
-      const int slot = tval_u[int64_t(s) * Tu + uentry[sb]];
-      const int pos = useg_off[int64_t(s) * (B + 1) + slot] + atomicAdd(&ucursor[int64_t(s) * B + slot], 1);
-      strip[int64_t(s) * B + pos] = b;
-    } else if (which == 1) {
-      slot_i[sb] = tval_i[int64_t(s) * Ti + slot_i[sb]];
-    } else {
-      slot_j[sb] = tval_i[int64_t(s) * Ti + slot_j[sb]];
+// one thread per segment: packed 32-byte header, written in PARTITIONED order -- GENERAL segments (touching a shared
+// item, or holding several triples of one user) occupy [0, ngen), FAST ones (one triple, both items singletons)
+// [ngen, nu) -- so each kernel walks a dense range.  header.w = 1 iff the segment touches a shared item.
+__global__ void prep_pack_kernel(int s0, int ns, int B, const int32_t* __restrict__ ucnt,
+                                 const int32_t* __restrict__ seg_user, const int32_t* __restrict__ seg_off,
+                                 const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_slow,
+                                 const int4* __restrict__ rec, int4* seg_hdr, int32_t* nslow, int32_t* nfast) {
+  const int64_t total = int64_t(ns) * B;
+  const unsigned lane = threadIdx.x & 31;
+  for (int64_t base = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) & ~int64_t(31); base < total;
+       base += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t tl = base + lane;
+    bool valid = tl < total;
+    int s = 0, seg = 0, nu = 0;
+    if (valid) { s = s0 + int(tl / B); seg = int(tl - int64_t(s - s0) * B); nu = ucnt[s]; valid = seg < nu; }
+    const int64_t t = int64_t(s) * B + seg;
+    const int shared = valid ? seg_slow[t] : 0;
+    int b0 = 0, b1 = 0;
+    if (valid) { b0 = seg_off[t]; b1 = b0 + seg_cnt[t]; }
+    const int slow = (shared || (b1 - b0) != 1) ? 1 : 0;
+    // warp-aggregated counters, one aggregation per distinct step present in the warp (at most 2 when B >= 32)
+    int k = -1;
+    unsigned todo = __ballot_sync(0xffffffffu, valid);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const int ls = __shfl_sync(0xffffffffu, s, leader);
+      const bool mine = valid && s == ls;
+      const unsigned m_slow = __ballot_sync(0xffffffffu, mine && slow);
+      const unsigned m_fast = __ballot_sync(0xffffffffu, mine && !slow);
+      int bs = 0, bf = 0;
+      if (int(lane) == leader) {
+        if (m_slow) bs = atomicAdd(&nslow[ls], __popc(m_slow));
+        if (m_fast) bf = atomicAdd(&nfast[ls], __popc(m_fast));
+      }
+      bs = __shfl_sync(0xffffffffu, bs, leader);
+      bf = __shfl_sync(0xffffffffu, bf, leader);
+      if (mine) {
+        const unsigned lt = (1u << lane) - 1u;
+        k = slow ? bs + __popc(m_slow & lt) : nu - 1 - (bf + __popc(m_fast & lt));
+      }
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (valid) {
+      int4* h = seg_hdr + (int64_t(s) * B + k) * 2;
+      h[0] = make_int4(seg_user[t], b0, b1 - b0, shared);
+      h[1] = rec[int64_t(s) * B + b0];
     }
   }
 }
@@ -209,15 +263,15 @@ __global__ void prep_scatter_kernel(int S, int B, int Tu, int Ti, const int32_t*
 // ------------------------------------------------------------------------------------------------
 struct StepCtx {
   float* P; float* Q; float* accP; float* accQ;
-  const int32_t* u; const int32_t* i; const int32_t* j;  // whole chunk [S*B]
   int d, B, S;
   float lr, kreg, reg_adv, eps;
   int adver;
-  // workspace
-  const int32_t* ucnt; const int32_t* icnt; const int32_t* useg_user; const int32_t* useg_off; const int32_t* strip;
-  const int32_t* slot_i; const int32_t* slot_j; const int32_t* iu_item;
+  const int32_t* ucnt; const int32_t* icnt; const int32_t* nslow;
+  const int4* seg_hdr; const int4* rec; const int32_t* iu_item;
   float* GQ; float* HQ; float* GP; float* cbuf;
   float* stats;  // nullable [S,2]
+  int flags;     // tuning switches (APR_STEP_FLAGS)
+  int s_begin, s_end;  // steps of this launch
 };
 
 template <int G, int V>
@@ -256,6 +310,18 @@ __device__ __forceinline__ float row_dot(const Row<G, V>& a, const Row<G, V>& b,
   for (int k = 0; k < V; ++k) s += f4_dot(a.v[k], b.v[k]);
   return group_sum<G>(s, mask);
 }
+template <int G, int V>
+__device__ __forceinline__ void row_zero(Row<G, V>& r) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) r.v[k] = f4_zero();
+}
+
+// single MUFU.RSQ (operands here are >= 1e-12, never denormal)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float softplus_neg(float r) {  // softplus(-r)
   return fmaxf(-r, 0.f) + log1pf(expf(-fabsf(r)));
@@ -265,26 +331,42 @@ __device__ __forceinline__ float bpr_coeff(float x, float& r_out) {
   const float r = fminf(fmaxf(x, -80.0f), 1e8f);
   r_out = r;
   const float m = (x >= -80.0f && x <= 1e8f) ? 1.0f : 0.0f;
-  return -m / (1.0f + expf(r));
+  return __fdividef(-m, 1.0f + expf(r));
 }
 
+// Adagrad on one row with the accumulator row already in registers
 template <int G, int V>
-__device__ __forceinline__ void adagrad_row(float* W, float* A, const Row<G, V>& w, const Row<G, V>& g, int lane, int d,
-                                            float lr) {
+__device__ __forceinline__ void adagrad_apply(float* W, float* A, const Row<G, V>& w, Row<G, V> a, const Row<G, V>& g,
+                                              int lane, int d, float lr) {
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const int e = (k * G + lane) * 4;
     if (e < d) {
-      float4 a = ldcg4(A + e);
       const float4 gg = g.v[k];
-      a.x = fmaf(gg.x, gg.x, a.x); a.y = fmaf(gg.y, gg.y, a.y); a.z = fmaf(gg.z, gg.z, a.z); a.w = fmaf(gg.w, gg.w, a.w);
+      float4 aa = a.v[k];
+      aa.x = fmaf(gg.x, gg.x, aa.x); aa.y = fmaf(gg.y, gg.y, aa.y); aa.z = fmaf(gg.z, gg.z, aa.z); aa.w = fmaf(gg.w, gg.w, aa.w);
       float4 nw = w.v[k];
-      nw.x -= lr * gg.x / sqrtf(a.x); nw.y -= lr * gg.y / sqrtf(a.y);
-      nw.z -= lr * gg.z / sqrtf(a.z); nw.w -= lr * gg.w / sqrtf(a.w);
-      stcg4(A + e, a);
+      // w -= lr g / sqrt(a): MUFU.RSQ (2 ulp) instead of IEEE sqrt + divide -- 6x fewer issue slots, still ~1e-7
+      nw.x = fmaf(-lr * gg.x, rsqrt_fast(aa.x), nw.x); nw.y = fmaf(-lr * gg.y, rsqrt_fast(aa.y), nw.y);
+      nw.z = fmaf(-lr * gg.z, rsqrt_fast(aa.z), nw.z); nw.w = fmaf(-lr * gg.w, rsqrt_fast(aa.w), nw.w);
+      stcg4(A + e, aa);
       stcg4(W + e, nw);
     }
   }
+}
+template <int G, int V>
+__device__ __forceinline__ void adagrad_row(float* W, float* A, const Row<G, V>& w, const Row<G, V>& g, int lane, int d,
+                                            float lr) {
+  Row<G, V> a;
+  row_load<G, V>(a, A, lane, d);
+  adagrad_apply<G, V>(W, A, w, a, g, lane, d, lr);
+}
+
+// eps * rsqrt(max(||G||^2, 1e-12))  (tf.nn.l2_normalize epsilon, APR.py:190-191)
+template <int G, int V>
+__device__ __forceinline__ float delta_scale(const Row<G, V>& g, float eps, unsigned mask) {
+  const float ss = row_dot<G, V>(g, g, mask);
+  return eps * rsqrt_fast(fmaxf(ss, 1e-12f));
 }
 
 // block-level accumulation of {loss, correct} into stats[2*s .. 2*s+1]
@@ -301,208 +383,460 @@ __device__ __forceinline__ void stats_flush(float* stats, int s, float loss, flo
   __syncthreads();
 }
 
-// phase 1 (adver=1): plain forward/backward.  fused=true (adver=0): complete BPR step for the user side.
-template <int G, int V, bool FUSED_BPR>
-__device__ __forceinline__ void phase_plain(const StepCtx& c, int s, int gid, int ngroups, int lane, unsigned mask) {
-  const int d = c.d, B = c.B;
-  const int nu = c.ucnt[s];
-  const int32_t* useg_user = c.useg_user + int64_t(s) * B;
-  const int32_t* useg_off = c.useg_off + int64_t(s) * (B + 1);
-  const int32_t* strip = c.strip + int64_t(s) * B;
-  const int32_t* ii = c.i + int64_t(s) * B;
-  const int32_t* jj = c.j + int64_t(s) * B;
-  const int32_t* slot_i = c.slot_i + int64_t(s) * B;
-  const int32_t* slot_j = c.slot_j + int64_t(s) * B;
-  float* acc_ws = FUSED_BPR ? c.HQ : c.GQ;
-  float loss = 0.f, correct = 0.f;
-  for (int seg = gid; seg < nu; seg += ngroups) {
-    const int user = useg_user[seg];
-    const int b0 = useg_off[seg], b1 = useg_off[seg + 1];
-    Row<G, V> p, g;
-    row_load<G, V>(p, c.P + int64_t(user) * d, lane, d);
+// item-row gradient sink: shared slot -> RED into the workspace; singleton -> Adagrad right here
+template <int G, int V>
+__device__ __forceinline__ void item_sink(const StepCtx& c, int item, int slot, const Row<G, V>& w, const Row<G, V>& g,
+                                          int lane, int d) {
+  if (slot >= 0) row_red<G, V>(g, c.HQ + int64_t(slot) * d, lane, d);
+  else adagrad_row<G, V>(c.Q + int64_t(item) * d, c.accQ + int64_t(item) * d, w, g, lane, d, c.lr);
+}
+
+// adversarial forward/backward of one triple given the plain coefficient cf and the row gradients gi, gj of its items
+// (from the workspace when shared, +-cf*p when singleton).  Accumulates the user gradient, sinks the item gradients.
+template <int G, int V>
+__device__ __forceinline__ void adv_triple(const StepCtx& c, const int4 rc, float cf, const Row<G, V>& p,
+                                           const Row<G, V>& pd, const Row<G, V>& q, const Row<G, V>& n, Row<G, V>& g,
+                                           int lane, int d, unsigned mask) {
+  Row<G, V> gi, gj;
+  if (rc.z >= 0) row_load<G, V>(gi, c.GQ + int64_t(rc.z) * d, lane, d);
+  else {
 #pragma unroll
-    for (int k = 0; k < V; ++k) g.v[k] = f4_zero();
+    for (int k = 0; k < V; ++k) gi.v[k] = f4_scale(p.v[k], cf);
+  }
+  if (rc.w >= 0) row_load<G, V>(gj, c.GQ + int64_t(rc.w) * d, lane, d);
+  else {
+#pragma unroll
+    for (int k = 0; k < V; ++k) gj.v[k] = f4_scale(p.v[k], -cf);
+  }
+  const float sci = delta_scale<G, V>(gi, c.eps, mask);
+  const float scj = delta_scale<G, V>(gj, c.eps, mask);
+  Row<G, V> qd, nd;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    qd.v[k] = f4_fma(sci, gi.v[k], q.v[k]);
+    nd.v[k] = f4_fma(scj, gj.v[k], n.v[k]);
+  }
+  const float xa = row_dot<G, V>(pd, qd, mask) - row_dot<G, V>(pd, nd, mask);
+  float ra;
+  const float ca = c.reg_adv * bpr_coeff(xa, ra);
+  Row<G, V> hi, hj;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    g.v[k] = f4_fma(ca, f4_sub(qd.v[k], nd.v[k]), g.v[k]);
+    g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
+    const float4 t = f4_fma(ca, pd.v[k], f4_scale(p.v[k], cf));  // c p + reg_adv c' (p + dP)
+    hi.v[k] = f4_fma(c.kreg, q.v[k], t);
+    hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(t, -1.f));
+  }
+  item_sink<G, V>(c, rc.x, rc.z, q, hi, lane, d);
+  item_sink<G, V>(c, rc.y, rc.w, n, hj, lane, d);
+}
+
+struct StepStats { float loss, correct; };
+
+// ---------------------------------------------------------------------------------------------------------
+// FAST segment: one triple, both items singletons.  Six row reads, six row writes, everything else in registers.
+// The adversarial forward is evaluated in closed form from four row reductions (S_pq, S_pn, S_pp, S_dd with
+// dq = q - n), which is the same arithmetic as APR.py:130-165 with the sums regrouped:
+//     G_P = c dq, G_i = c p = -G_j             (plain gradients, APR.py:183-187)
+//     a = eps c rsqrt(max(c^2 S_dd, 1e-12))    (Delta_P = a dq)       b = eps c rsqrt(max(c^2 S_pp, 1e-12))  (Delta_i = b p)
+//     x' = <p + a dq, (q + b p) - (n - b p)> = x + 2 b S_pp + a S_dd + 2 a b x
+//     g_P = (c + c') dq + (2 c' b + k) p       t = (c + c') p + c' a dq       g_i = t + k q       g_j = k n - t
+// with c' = reg_adv * coeff(x').  FULL = row width equals d (no tail predicates).
+// ---------------------------------------------------------------------------------------------------------
+template <int G, int V, bool FULL>
+__device__ __forceinline__ void fast_segment(const StepCtx& c, const int user, const int item_i, const int item_j, int lane,
+                                             unsigned mask, StepStats& st) {
+  const int d = c.d;
+  float* Pu = c.P + int64_t(user) * d;
+  float* Au = c.accP + int64_t(user) * d;
+  float* Qi = c.Q + int64_t(item_i) * d;
+  float* Ai = c.accQ + int64_t(item_i) * d;
+  float* Qj = c.Q + int64_t(item_j) * d;
+  float* Aj = c.accQ + int64_t(item_j) * d;
+  float4 p[V], q[V], n[V], ap[V], ai[V], aj[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int e = (k * G + lane) * 4;
+    const bool ok = FULL || e < d;
+    p[k] = ok ? ldcg4(Pu + e) : f4_zero();
+    q[k] = ok ? ldcg4(Qi + e) : f4_zero();
+    n[k] = ok ? ldcg4(Qj + e) : f4_zero();
+    ap[k] = ok ? ldcg4(Au + e) : f4_zero();
+    ai[k] = ok ? ldcg4(Ai + e) : f4_zero();
+    aj[k] = ok ? ldcg4(Aj + e) : f4_zero();
+  }
+  float s_pq = 0.f, s_pn = 0.f, s_pp = 0.f, s_dd = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    s_pq += f4_dot(p[k], q[k]);
+    s_pn += f4_dot(p[k], n[k]);
+    s_pp += f4_dot(p[k], p[k]);
+    const float4 dq = f4_sub(q[k], n[k]);
+    s_dd += f4_dot(dq, dq);
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {  // four independent butterflies, interleaved
+    s_pq += __shfl_xor_sync(mask, s_pq, o);
+    s_pn += __shfl_xor_sync(mask, s_pn, o);
+    s_pp += __shfl_xor_sync(mask, s_pp, o);
+    s_dd += __shfl_xor_sync(mask, s_dd, o);
+  }
+  const float x = s_pq - s_pn;
+  float r;
+  const float cf = bpr_coeff(x, r);
+  if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+  float A = cf, Bc = c.kreg, Cc = 0.f;
+  if (c.adver) {
+    const float a = c.eps * cf * rsqrt_fast(fmaxf(cf * cf * s_dd, 1e-12f));
+    const float b = c.eps * cf * rsqrt_fast(fmaxf(cf * cf * s_pp, 1e-12f));
+    const float xa = x + 2.f * b * s_pp + a * s_dd + 2.f * a * b * x;
+    float ra;
+    const float ca = c.reg_adv * bpr_coeff(xa, ra);
+    A = cf + ca;
+    Bc = 2.f * ca * b + c.kreg;
+    Cc = ca * a;
+  }
+  const float kreg = c.kreg, lr = c.lr;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int e = (k * G + lane) * 4;
+    if (FULL || e < d) {
+      const float4 dq = f4_sub(q[k], n[k]);
+      const float4 gp = f4_fma(A, dq, f4_scale(p[k], Bc));
+      const float4 t = f4_fma(A, p[k], f4_scale(dq, Cc));
+      const float4 gi = f4_fma(kreg, q[k], t);
+      const float4 gj = f4_fma(kreg, n[k], f4_scale(t, -1.f));
+      float4 a0 = ap[k], a1 = ai[k], a2 = aj[k], w0 = p[k], w1 = q[k], w2 = n[k];
+#define APR_ADAGRAD_LANE(acc, w, g, f)            \
+  acc.f = fmaf(g.f, g.f, acc.f);                  \
+  w.f = fmaf(-lr * g.f, rsqrt_fast(acc.f), w.f);
+      APR_ADAGRAD_LANE(a0, w0, gp, x) APR_ADAGRAD_LANE(a0, w0, gp, y) APR_ADAGRAD_LANE(a0, w0, gp, z) APR_ADAGRAD_LANE(a0, w0, gp, w)
+      APR_ADAGRAD_LANE(a1, w1, gi, x) APR_ADAGRAD_LANE(a1, w1, gi, y) APR_ADAGRAD_LANE(a1, w1, gi, z) APR_ADAGRAD_LANE(a1, w1, gi, w)
+      APR_ADAGRAD_LANE(a2, w2, gj, x) APR_ADAGRAD_LANE(a2, w2, gj, y) APR_ADAGRAD_LANE(a2, w2, gj, z) APR_ADAGRAD_LANE(a2, w2, gj, w)
+#undef APR_ADAGRAD_LANE
+      stcg4(Au + e, a0); stcg4(Pu + e, w0);
+      stcg4(Ai + e, a1); stcg4(Qi + e, w1);
+      stcg4(Aj + e, a2); stcg4(Qj + e, w2);
+    }
+  }
+}
+
+// fast segments k in [k0, k1) of the partitioned header array; one lane group per segment, grid-stride
+template <int G, int V, bool FULL>
+__device__ __forceinline__ void fast_range(const StepCtx& c, int s, int k0, int k1, int gid, int ngroups, int lane,
+                                           unsigned mask, StepStats& st) {
+  const int4* seg_hdr = c.seg_hdr + int64_t(s) * c.B * 2;
+  for (int k = k0 + gid; k < k1; k += ngroups) {
+    const int user = __ldg(&seg_hdr[2 * k].x);
+    const int2 ij = __ldg(reinterpret_cast<const int2*>(&seg_hdr[2 * k + 1]));
+    fast_segment<G, V, FULL>(c, user, ij.x, ij.y, lane, mask, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GENERAL segments (shared items and/or several triples of one user)
+// ---------------------------------------------------------------------------------------------------------
+// A complete step for a general segment that touches NO shared item (several triples of one user), or a complete
+// BPR step for any segment (shared item gradients then go through item_sink's RED).
+template <int G, int V>
+__device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0, const int4 h1, const int4* rec, int lane,
+                                                 unsigned mask, StepStats& st) {
+  const int d = c.d;
+  const bool adver = c.adver != 0;
+  const int user = h0.x;
+  const int b0 = h0.y, b1 = h0.y + h0.z;
+  float* Pu = c.P + int64_t(user) * d;
+  float* Au = c.accP + int64_t(user) * d;
+  Row<G, V> p, g;
+  row_load<G, V>(p, Pu, lane, d);
+  row_zero<G, V>(g);
+  int4 rc = h1;
+  for (int pos = b0; pos < b1; ++pos) {
+    if (pos > b0) rc = rec[pos];
+    Row<G, V> q, n;
+    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
+    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
+    float r;
+    const float cf = bpr_coeff(x, r);
+    if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+#pragma unroll
+    for (int k = 0; k < V; ++k) g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]);
+    if (!adver) {
+      Row<G, V> hi, hj;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
+        hi.v[k] = f4_fma(c.kreg, q.v[k], f4_scale(p.v[k], cf));
+        hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(p.v[k], -cf));
+      }
+      item_sink<G, V>(c, rc.x, rc.z, q, hi, lane, d);
+      item_sink<G, V>(c, rc.y, rc.w, n, hj, lane, d);
+    }
+  }
+  if (adver) {
+    // second pass right away: Delta from the local gradients (x, c recomputed: same bits)
+    const float sp = delta_scale<G, V>(g, c.eps, mask);
+    Row<G, V> pd;
+#pragma unroll
+    for (int k = 0; k < V; ++k) pd.v[k] = f4_fma(sp, g.v[k], p.v[k]);
+    rc = h1;
     for (int pos = b0; pos < b1; ++pos) {
-      const int b = strip[pos];
-      const int it = ii[b], jt = jj[b], si = slot_i[b], sj = slot_j[b];
+      if (pos > b0) rc = rec[pos];
       Row<G, V> q, n;
-      row_load<G, V>(q, c.Q + int64_t(it) * d, lane, d);
-      row_load<G, V>(n, c.Q + int64_t(jt) * d, lane, d);
+      row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
+      row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
       const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
       float r;
       const float cf = bpr_coeff(x, r);
-      if (c.stats) { loss += softplus_neg(r); correct += (x > 0.f) ? 1.f : 0.f; }
-      Row<G, V> hi, hj;
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]);
-        hi.v[k] = f4_scale(p.v[k], cf);
-        hj.v[k] = f4_scale(p.v[k], -cf);
-        if (FUSED_BPR) {
-          g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
-          hi.v[k] = f4_fma(c.kreg, q.v[k], hi.v[k]);
-          hj.v[k] = f4_fma(c.kreg, n.v[k], hj.v[k]);
-        }
-      }
-      row_red<G, V>(hi, acc_ws + int64_t(si) * d, lane, d);
-      row_red<G, V>(hj, acc_ws + int64_t(sj) * d, lane, d);
-      if (!FUSED_BPR && lane == 0) c.cbuf[pos] = cf;
+      adv_triple<G, V>(c, rc, cf, p, pd, q, n, g, lane, d, mask);
     }
-    if (FUSED_BPR) adagrad_row<G, V>(c.P + int64_t(user) * d, c.accP + int64_t(user) * d, p, g, lane, d, c.lr);
-    else row_store<G, V>(g, c.GP + int64_t(seg) * d, lane, d);
   }
-  if (c.stats) stats_flush(c.stats, s, loss, correct, lane == 0);
+  adagrad_row<G, V>(Pu, Au, p, g, lane, d, c.lr);
 }
 
-// eps * rsqrt(max(||G||^2, 1e-12))  (tf.nn.l2_normalize epsilon, APR.py:190-191)
+// APR stage 0 for one segment that touches a shared item: plain forward/backward; publishes G_P[k], c per triple, G_Q.
 template <int G, int V>
-__device__ __forceinline__ float delta_scale(const Row<G, V>& g, float eps, unsigned mask) {
-  const float ss = row_dot<G, V>(g, g, mask);
-  return eps / sqrtf(fmaxf(ss, 1e-12f));
-}
-
-template <int G, int V>
-__device__ __forceinline__ void phase_adv(const StepCtx& c, int s, int gid, int ngroups, int lane, unsigned mask) {
-  const int d = c.d, B = c.B;
-  const int nu = c.ucnt[s];
-  const int32_t* useg_user = c.useg_user + int64_t(s) * B;
-  const int32_t* useg_off = c.useg_off + int64_t(s) * (B + 1);
-  const int32_t* strip = c.strip + int64_t(s) * B;
-  const int32_t* ii = c.i + int64_t(s) * B;
-  const int32_t* jj = c.j + int64_t(s) * B;
-  const int32_t* slot_i = c.slot_i + int64_t(s) * B;
-  const int32_t* slot_j = c.slot_j + int64_t(s) * B;
-  for (int seg = gid; seg < nu; seg += ngroups) {
-    const int user = useg_user[seg];
-    const int b0 = useg_off[seg], b1 = useg_off[seg + 1];
-    Row<G, V> p, g, pd;
-    row_load<G, V>(p, c.P + int64_t(user) * d, lane, d);
-    row_load<G, V>(g, c.GP + int64_t(seg) * d, lane, d);
-    const float sp = delta_scale<G, V>(g, c.eps, mask);
+__device__ __forceinline__ void slow_plain(const StepCtx& c, int k0, const int4 h0, const int4 h1, const int4* rec, int lane,
+                                           unsigned mask, StepStats& st) {
+  const int d = c.d;
+  const int b0 = h0.y, b1 = h0.y + h0.z;
+  Row<G, V> p, g;
+  row_load<G, V>(p, c.P + int64_t(h0.x) * d, lane, d);
+  row_zero<G, V>(g);
+  int4 rc = h1;
+  for (int pos = b0; pos < b1; ++pos) {
+    if (pos > b0) rc = rec[pos];
+    Row<G, V> q, n;
+    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
+    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
+    float r;
+    const float cf = bpr_coeff(x, r);
+    if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+    Row<G, V> t;
 #pragma unroll
-    for (int k = 0; k < V; ++k) pd.v[k] = f4_fma(sp, g.v[k], p.v[k]);
-    for (int pos = b0; pos < b1; ++pos) {
-      const int b = strip[pos];
-      const int it = ii[b], jt = jj[b], si = slot_i[b], sj = slot_j[b];
-      const float cf = __ldcg(&c.cbuf[pos]);
-      Row<G, V> q, n, gi, gj;
-      row_load<G, V>(q, c.Q + int64_t(it) * d, lane, d);
-      row_load<G, V>(n, c.Q + int64_t(jt) * d, lane, d);
-      row_load<G, V>(gi, c.GQ + int64_t(si) * d, lane, d);
-      row_load<G, V>(gj, c.GQ + int64_t(sj) * d, lane, d);
-      const float sci = delta_scale<G, V>(gi, c.eps, mask);
-      const float scj = delta_scale<G, V>(gj, c.eps, mask);
-      Row<G, V> qd, nd;
+    for (int k = 0; k < V; ++k) { g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]); t.v[k] = f4_scale(p.v[k], cf); }
+    if (rc.z >= 0) row_red<G, V>(t, c.GQ + int64_t(rc.z) * d, lane, d);
+    if (rc.w >= 0) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        qd.v[k] = f4_fma(sci, gi.v[k], q.v[k]);
-        nd.v[k] = f4_fma(scj, gj.v[k], n.v[k]);
-      }
-      const float xa = row_dot<G, V>(pd, qd, mask) - row_dot<G, V>(pd, nd, mask);
-      float ra;
-      const float ca = c.reg_adv * bpr_coeff(xa, ra);
-      Row<G, V> hi, hj;
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        g.v[k] = f4_fma(ca, f4_sub(qd.v[k], nd.v[k]), g.v[k]);
-        g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
-        const float4 t = f4_fma(ca, pd.v[k], f4_scale(p.v[k], cf));  // c p + reg_adv c' (p + dP)
-        hi.v[k] = f4_fma(c.kreg, q.v[k], t);
-        hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(t, -1.f));
-      }
-      row_red<G, V>(hi, c.HQ + int64_t(si) * d, lane, d);
-      row_red<G, V>(hj, c.HQ + int64_t(sj) * d, lane, d);
+      for (int k = 0; k < V; ++k) t.v[k] = f4_scale(t.v[k], -1.f);
+      row_red<G, V>(t, c.GQ + int64_t(rc.w) * d, lane, d);
     }
-    adagrad_row<G, V>(c.P + int64_t(user) * d, c.accP + int64_t(user) * d, p, g, lane, d, c.lr);
+    if (lane == 0) c.cbuf[pos] = cf;
   }
+  row_store<G, V>(g, c.GP + int64_t(k0) * d, lane, d);
 }
 
+// APR stage 1 for one segment that touches a shared item: Delta from the batch-wide sums, adversarial pass, Adagrad on
+// the rows this segment owns (user row, singleton item rows); shared item gradients are RED into H_Q.
 template <int G, int V>
-__device__ __forceinline__ void phase_items(const StepCtx& c, int s, int gid, int ngroups, int lane) {
+__device__ __forceinline__ void slow_adv(const StepCtx& c, int k0, const int4 h0, const int4 h1, const int4* rec, int lane,
+                                         unsigned mask) {
+  const int d = c.d;
+  const int b0 = h0.y, b1 = h0.y + h0.z;
+  int4 rc = h1;
+  Row<G, V> p, g, pd;
+  row_load<G, V>(p, c.P + int64_t(h0.x) * d, lane, d);
+  row_load<G, V>(g, c.GP + int64_t(k0) * d, lane, d);
+  const float sp = delta_scale<G, V>(g, c.eps, mask);
+#pragma unroll
+  for (int k = 0; k < V; ++k) pd.v[k] = f4_fma(sp, g.v[k], p.v[k]);
+  for (int pos = b0; pos < b1; ++pos) {
+    if (pos > b0) rc = rec[pos];
+    const float cf = __ldcg(&c.cbuf[pos]);
+    Row<G, V> q, n;
+    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
+    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    adv_triple<G, V>(c, rc, cf, p, pd, q, n, g, lane, d, mask);
+  }
+  adagrad_row<G, V>(c.P + int64_t(h0.x) * d, c.accP + int64_t(h0.x) * d, p, g, lane, d, c.lr);
+}
+
+// stage 2: shared item slots
+template <int G, int V>
+__device__ __forceinline__ void items_shared(const StepCtx& c, int s, int gid, int ngroups, int lane) {
   const int d = c.d, B = c.B;
   const int ni = c.icnt[s];
-  const int32_t* iu_item = c.iu_item + int64_t(s) * 2 * B;
+  const int32_t* iu_item = c.iu_item + int64_t(s) * B;
   Row<G, V> z;
-#pragma unroll
-  for (int k = 0; k < V; ++k) z.v[k] = f4_zero();
+  row_zero<G, V>(z);
   for (int slot = gid; slot < ni; slot += ngroups) {
     const int item = iu_item[slot];
-    Row<G, V> w, g;
+    Row<G, V> w, g, a;
     row_load<G, V>(g, c.HQ + int64_t(slot) * d, lane, d);
     row_load<G, V>(w, c.Q + int64_t(item) * d, lane, d);
-    adagrad_row<G, V>(c.Q + int64_t(item) * d, c.accQ + int64_t(item) * d, w, g, lane, d, c.lr);
+    row_load<G, V>(a, c.accQ + int64_t(item) * d, lane, d);
+    adagrad_apply<G, V>(c.Q + int64_t(item) * d, c.accQ + int64_t(item) * d, w, a, g, lane, d, c.lr);
     row_store<G, V>(z, c.HQ + int64_t(slot) * d, lane, d);
     if (c.adver) row_store<G, V>(z, c.GQ + int64_t(slot) * d, lane, d);
   }
 }
 
+// The stages of the GENERAL path for one step (grid-wide ordering between them):
+//   stage 0 (APR)  segments with a shared item: slow_plain
+//   stage 1        APR: slow_adv for those, segment_complete for the rest;  BPR: segment_complete for all
+//   stage 2        items_shared
+template <int G, int V>
+__device__ __forceinline__ void general_stage(const StepCtx& c, int s, int stage, int gid, int ngroups, int lane,
+                                              unsigned mask, StepStats& st) {
+  const int B = c.B;
+  if (stage == 2) { items_shared<G, V>(c, s, gid, ngroups, lane); return; }
+  const int ng = c.nslow[s];
+  const int4* seg_hdr = c.seg_hdr + int64_t(s) * B * 2;
+  const int4* rec = c.rec + int64_t(s) * B;
+  for (int k0 = gid; k0 < ng; k0 += ngroups) {
+    const int4 h0 = __ldg(&seg_hdr[2 * k0]);
+    const int4 h1 = __ldg(&seg_hdr[2 * k0 + 1]);
+    const bool shared = h0.w != 0;
+    if (stage == 0) {
+      if (shared) slow_plain<G, V>(c, k0, h0, h1, rec, lane, mask, st);
+    } else if (shared && c.adver) {
+      slow_adv<G, V>(c, k0, h0, h1, rec, lane, mask);
+    } else {
+      segment_complete<G, V>(c, h0, h1, rec, lane, mask, st);
+    }
+  }
+}
+
 constexpr int kThreads = 256;
 
-template <int G, int V, int PHASE>
-__global__ void __launch_bounds__(kThreads) step_phase_kernel(StepCtx c, int s) {
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  const unsigned wl = threadIdx.x & 31;
+  return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+}
+
+// mode 0: general-path stage kernel (small grid) ...
+template <int G, int V>
+__global__ void __launch_bounds__(kThreads) general_stage_kernel(StepCtx c, int s, int stage) {
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
-  const unsigned wl = threadIdx.x & 31;
-  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
-  if (PHASE == 0) phase_plain<G, V, true>(c, s, gid, ngroups, lane, mask);
-  if (PHASE == 1) phase_plain<G, V, false>(c, s, gid, ngroups, lane, mask);
-  if (PHASE == 2) phase_adv<G, V>(c, s, gid, ngroups, lane, mask);
-  if (PHASE == 3) phase_items<G, V>(c, s, gid, ngroups, lane);
+  StepStats st = {0.f, 0.f};
+  if (stage == 0 && !(c.adver && c.icnt[s] > 0)) return;
+  general_stage<G, V>(c, s, stage, gid, ngroups, lane, group_mask<G>(), st);
+  if (c.stats && stage < 2) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
 }
 
-// all steps in one cooperative launch
-template <int G, int V>
+// ... and the fast-path kernel, launched on a second stream so that the general path's load chains hide under it
+template <int G, int V, bool FULL>
+__global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fast_kernel(StepCtx c, int s) {
+  const int lane = threadIdx.x % G;
+  const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
+  const int ngroups = gridDim.x * (kThreads / G);
+  StepStats st = {0.f, 0.f};
+  fast_range<G, V, FULL>(c, s, c.nslow[s], c.ucnt[s], gid, ngroups, lane, group_mask<G>(), st);
+  if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+}
+
+// mode 1: all steps in one cooperative launch; the general stages run under the two halves of the fast range
+template <int G, int V, bool FULL>
 __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
-  const unsigned wl = threadIdx.x & 31;
-  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
-  for (int s = 0; s < c.S; ++s) {
-    if (c.adver) {
-      phase_plain<G, V, false>(c, s, gid, ngroups, lane, mask);
+  const unsigned mask = group_mask<G>();
+  for (int s = c.s_begin; s < c.s_end; ++s) {
+    const int nu = c.ucnt[s], ng = c.nslow[s];
+    const bool shared = c.icnt[s] > 0;  // grid-uniform
+    const int mid = ng + (nu - ng + 1) / 2;
+    StepStats st = {0.f, 0.f};
+    if (shared && c.adver) {
+      general_stage<G, V>(c, s, 0, gid, ngroups, lane, mask, st);
       grid.sync();
-      phase_adv<G, V>(c, s, gid, ngroups, lane, mask);
-    } else {
-      phase_plain<G, V, true>(c, s, gid, ngroups, lane, mask);
     }
-    grid.sync();
-    phase_items<G, V>(c, s, gid, ngroups, lane);
+    general_stage<G, V>(c, s, 1, gid, ngroups, lane, mask, st);
+    fast_range<G, V, FULL>(c, s, ng, mid, gid, ngroups, lane, mask, st);
+    if (shared) {
+      grid.sync();  // every H_Q contribution must have landed before the shared rows are updated
+      general_stage<G, V>(c, s, 2, gid, ngroups, lane, mask, st);
+    }
+    fast_range<G, V, FULL>(c, s, mid, nu, gid, ngroups, lane, mask, st);
+    if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
     grid.sync();
   }
 }
 
-template <int G, int V>
-static int run_steps(const StepCtx& c, int mode, cudaStream_t st) {
+// second stream + events for the fork/join of mode 0 (created once per process; no device memory)
+struct AuxStream {
+  cudaStream_t stream = nullptr;       // fast-path kernels of mode 0
+  cudaStream_t prep_stream = nullptr;  // index preparation, pipelined one sub-chunk ahead of the step kernels
+  cudaEvent_t fork = nullptr, join = nullptr, entry = nullptr;
+  std::vector<cudaEvent_t> prep_done;
+  bool ok = false;
+  cudaEvent_t prep_event(size_t k) {
+    while (prep_done.size() <= k) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      prep_done.push_back(e);
+    }
+    return prep_done[k];
+  }
+};
+static AuxStream& aux_stream() {
+  static AuxStream a;
+  if (!a.ok) {
+    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&a.prep_stream, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming) == cudaSuccess)
+      a.ok = true;
+  }
+  return a;
+}
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int G, int V, bool FULL>
+static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
   const int gpb = kThreads / G;
   const int sms = sm_count();
   if (mode == 0) {
-    const int cap = sms * 8;
-    const int grid_u = max(1, min((c.B + gpb - 1) / gpb, cap));
-    const int grid_i = max(1, min((2 * c.B + gpb - 1) / gpb, cap));
-    for (int s = 0; s < c.S; ++s) {
-      if (c.adver) {
-        step_phase_kernel<G, V, 1><<<grid_u, kThreads, 0, st>>>(c, s);
-        step_phase_kernel<G, V, 2><<<grid_u, kThreads, 0, st>>>(c, s);
-      } else {
-        step_phase_kernel<G, V, 0><<<grid_u, kThreads, 0, st>>>(c, s);
-      }
-      step_phase_kernel<G, V, 3><<<grid_i, kThreads, 0, st>>>(c, s);
+    AuxStream& ax = aux_stream();
+    if (!ax.ok) return APR_E_CUDA;
+    int occ_fast = 0;
+    APR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, fast_kernel<G, V, FULL>, kThreads, 0));
+    // resident blocks per SM are shared between the fast kernel and the general-path kernels running next to it
+    static const int fast_bps = env_int("APR_FAST_BLOCKS", 0), gen_bps = env_int("APR_GEN_BLOCKS", 0);
+    const int fb = fast_bps > 0 ? fast_bps : std::max(1, std::min(2, occ_fast));  // 16 warps/SM already saturate HBM
+    const int gb = gen_bps > 0 ? gen_bps : 2;
+    const int grid_fast = std::max(1, std::min((c.B + gpb - 1) / gpb, sms * fb));
+    const int grid_gen = std::max(1, std::min((c.B + gpb - 1) / gpb, sms * gb));
+    for (int s = c.s_begin; s < c.s_end; ++s) {
+      APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
+      APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
+      fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.stream>>>(c, s);
+      APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+      if (c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 0);
+      general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 1);
+      general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 2);
+      APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
     }
     APR_LAUNCH_CHECK();
     return APR_OK;
   }
   int occ = 0;
-  APR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_persistent_kernel<G, V>, kThreads, 0));
+  APR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_persistent_kernel<G, V, FULL>, kThreads, 0));
   if (occ < 1) return APR_E_CUDA;
   int grid = sms * occ;
-  grid = max(1, min(grid, (2 * c.B + gpb - 1) / gpb));
+  grid = std::max(1, std::min(grid, (c.B + gpb - 1) / gpb));
   StepCtx cc = c;
   void* args[] = {&cc};
-  APR_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)step_persistent_kernel<G, V>, dim3(grid), dim3(kThreads), args, 0, st));
+  APR_CUDA_CHECK(
+      cudaLaunchCooperativeKernel((void*)step_persistent_kernel<G, V, FULL>, dim3(grid), dim3(kThreads), args, 0, st));
   return APR_OK;
+}
+
+template <int G, int V>
+static int run_steps(const StepCtx& c, int mode, cudaStream_t st) {
+  if (c.d == G * V * 4) return run_steps_t<G, V, true>(c, mode, st);
+  return run_steps_t<G, V, false>(c, mode, st);
 }
 
 static int dispatch_steps(const StepCtx& c, int mode, cudaStream_t st) {
@@ -528,8 +862,7 @@ __global__ void __launch_bounds__(kThreads) loss_acc_kernel(const float* __restr
   const int s = blockIdx.x / tiles_per_step;
   const int tile = blockIdx.x - s * tiles_per_step;
   const int lane = threadIdx.x % G, g = threadIdx.x / G;
-  const unsigned wl = threadIdx.x & 31;
-  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl / G * G));
+  const unsigned mask = group_mask<G>();
   const int b_end = min(B, (tile + 1) * kTile);
   float loss = 0.f;
   int correct = 0;
@@ -562,6 +895,60 @@ static int run_loss_acc(const float* P, const float* Q, int d, const int32_t* u,
   return APR_OK;
 }
 
+// index preparation of the steps [s0, s0+ns) (one L2-sized sub-chunk) on stream st
+static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, const TrainLayout& L, int s0, int ns,
+                       int64_t rows_p, int64_t rows_q, void* ws, cudaStream_t st) {
+  const int B = L.B;
+  int32_t* tkey_u = at<int32_t>(ws, L.off_tkey_u);
+  int32_t* tval_u = at<int32_t>(ws, L.off_tval_u);
+  int32_t* tkey_i = at<int32_t>(ws, L.off_tkey_i);
+  int32_t* tval_i = at<int32_t>(ws, L.off_tval_i);
+  const int threads = 256;
+  const int64_t cap = int64_t(sm_count()) * 16;
+  // table keys = -1, table values = 0
+  APR_CUDA_CHECK(cudaMemsetAsync(tkey_u, 0xFF, size_t(int64_t(ns) * L.Tu * 4), st));
+  APR_CUDA_CHECK(cudaMemsetAsync(tval_u, 0, size_t(int64_t(ns) * L.Tu * 4), st));
+  APR_CUDA_CHECK(cudaMemsetAsync(tkey_i, 0xFF, size_t(int64_t(ns) * L.Ti * 4), st));
+  APR_CUDA_CHECK(cudaMemsetAsync(tval_i, 0, size_t(int64_t(ns) * L.Ti * 4), st));
+  const int64_t nt = int64_t(ns) * B;
+  const int grid_a = int(std::max<int64_t>(1, std::min<int64_t>((nt + threads - 1) / threads, cap)));
+  prep_insert_kernel<<<grid_a, threads, 0, st>>>(u, i, j, s0, ns, B, rows_p, rows_q, L.Tu, L.Ti, tkey_u, tval_u, tkey_i,
+                                                 tval_i, at<int32_t>(ws, L.off_entry), at<int32_t>(ws, L.off_hdr));
+  const int64_t ne = int64_t(ns) * (L.Tu + L.Ti);
+  const int grid_b = int(std::max<int64_t>(1, std::min<int64_t>((ne + threads - 1) / threads, cap)));
+  prep_compact_kernel<<<grid_b, threads, 0, st>>>(
+      s0, ns, B, L.Tu, L.Ti, tkey_u, tval_u, tkey_i, tval_i, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_icnt),
+      at<int32_t>(ws, L.off_iall), at<int32_t>(ws, L.off_tcursor), at<int32_t>(ws, L.off_seg_user),
+      at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt), at<int32_t>(ws, L.off_ucursor),
+      at<int32_t>(ws, L.off_iu_item));
+  prep_scatter_kernel<<<grid_a, threads, 0, st>>>(i, j, s0, ns, B, L.Tu, L.Ti, tval_u, tval_i, at<int32_t>(ws, L.off_entry),
+                                                  at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_ucursor),
+                                                  at<int4>(ws, L.off_rec), at<int32_t>(ws, L.off_seg_slow));
+  prep_pack_kernel<<<grid_a, threads, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_seg_user),
+                                               at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
+                                               at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
+                                               at<int4>(ws, L.off_seg_hdr), at<int32_t>(ws, L.off_nslow),
+                                               at<int32_t>(ws, L.off_nfast));
+  APR_LAUNCH_CHECK();
+  return APR_OK;
+}
+
+static int prepare_clear(const TrainLayout& L, void* ws, cudaStream_t st) {
+  // per-step counters and slow flags = 0
+  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_ucnt), 0, size_t(L.off_seg_user - L.off_ucnt), st));
+  return APR_OK;
+}
+
+static int prepare_impl(const int32_t* u, const int32_t* i, const int32_t* j, int S, int B, int d, int64_t rows_p,
+                        int64_t rows_q, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const TrainLayout L = make_layout(S, B, d);
+  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  int rc = prepare_clear(L, ws, st);
+  for (int s0 = 0; s0 < S && !rc; s0 += L.Sc)
+    rc = prepare_sub(u, i, j, L, s0, std::min(L.Sc, S - s0), rows_p, rows_q, ws, st);
+  return rc;
+}
+
 }  // namespace apr
 
 using namespace apr;
@@ -579,44 +966,10 @@ int apr_train_workspace_init(void* ws, int64_t ws_bytes, apr_stream_t stream) {
   return APR_OK;
 }
 
-static int prepare_impl(const int32_t* u, const int32_t* i, const int32_t* j, int S, int B, int d, int64_t rows_p,
-                        int64_t rows_q, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
-  // tables: keys = -1, values = 0; counts = 0
-  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_ucnt), 0, size_t(L.off_useg_user - L.off_ucnt), st));
-  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_tkey_u), 0xFF, size_t(int64_t(S) * L.Tu * 4), st));
-  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_tval_u), 0, size_t(int64_t(S) * L.Tu * 4), st));
-  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_tkey_i), 0xFF, size_t(int64_t(S) * L.Ti * 4), st));
-  const int64_t n3 = int64_t(S) * 3 * B;
-  const int threads = 256;
-  const int cap = sm_count() * 16;
-  const int grid_a = int(std::min<int64_t>((n3 + threads - 1) / threads, int64_t(cap)));
-  prep_insert_kernel<<<grid_a, threads, 0, st>>>(u, i, j, S, B, rows_p, rows_q, L.Tu, L.Ti, at<int32_t>(ws, L.off_tkey_u),
-                                                 at<int32_t>(ws, L.off_tval_u), at<int32_t>(ws, L.off_tkey_i),
-                                                 at<int32_t>(ws, L.off_uentry), at<int32_t>(ws, L.off_slot_i),
-                                                 at<int32_t>(ws, L.off_slot_j), at<int32_t>(ws, L.off_hdr));
-  const int64_t nt = int64_t(S) * (L.Tu + L.Ti);
-  const int grid_b = int(std::min<int64_t>((nt + threads - 1) / threads, int64_t(cap)));
-  prep_compact_kernel<<<grid_b, threads, 0, st>>>(S, B, L.Tu, L.Ti, at<int32_t>(ws, L.off_tkey_u),
-                                                  at<int32_t>(ws, L.off_tval_u), at<int32_t>(ws, L.off_tkey_i),
-                                                  at<int32_t>(ws, L.off_tval_i), at<int32_t>(ws, L.off_ucnt),
-                                                  at<int32_t>(ws, L.off_icnt), at<int32_t>(ws, L.off_useg_user),
-                                                  at<int32_t>(ws, L.off_ucursor), at<int32_t>(ws, L.off_iu_item));
-  prep_scan_kernel<<<S, 256, 0, st>>>(B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_ucursor),
-                                      at<int32_t>(ws, L.off_useg_off));
-  prep_scatter_kernel<<<grid_a, threads, 0, st>>>(S, B, L.Tu, L.Ti, at<int32_t>(ws, L.off_tval_u),
-                                                  at<int32_t>(ws, L.off_tval_i), at<int32_t>(ws, L.off_uentry),
-                                                  at<int32_t>(ws, L.off_useg_off), at<int32_t>(ws, L.off_ucursor),
-                                                  at<int32_t>(ws, L.off_strip), at<int32_t>(ws, L.off_slot_i),
-                                                  at<int32_t>(ws, L.off_slot_j));
-  APR_LAUNCH_CHECK();
-  return APR_OK;
-}
-
 int apr_train_prepare(const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, int32_t d, int64_t rows_p,
                       int64_t rows_q, void* ws, int64_t ws_bytes, apr_stream_t stream) {
   if (!u || !i || !j || !ws || S < 1 || B < 1 || rows_p < 1 || rows_q < 1 || !valid_dim(d)) return APR_E_ARG;
+  if (!aligned16(ws)) return APR_E_ALIGN;
   return prepare_impl(u, i, j, S, B, d, rows_p, rows_q, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -629,6 +982,29 @@ static int check_train_args(const float* P, const float* Q, const float* accP, c
   return APR_OK;
 }
 
+static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, int32_t S, int32_t B, float lr, float reg,
+                     float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, const TrainLayout& L, float* stats,
+                     int s_begin, int s_end, cudaStream_t st) {
+  StepCtx c;
+  c.P = P; c.Q = Q; c.accP = accP; c.accQ = accQ;
+  c.d = d; c.B = B; c.S = S;
+  c.lr = lr;
+  // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
+  c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
+  c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
+  c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt);
+  c.nslow = at<int32_t>(ws, L.off_nslow);
+  c.seg_hdr = at<int4>(ws, L.off_seg_hdr);
+  c.rec = at<int4>(ws, L.off_rec);
+  c.iu_item = at<int32_t>(ws, L.off_iu_item);
+  c.GQ = at<float>(ws, L.off_GQ); c.HQ = at<float>(ws, L.off_HQ); c.GP = at<float>(ws, L.off_GP);
+  c.cbuf = at<float>(ws, L.off_cbuf);
+  c.stats = stats;
+  c.flags = env_int("APR_STEP_FLAGS", 0);
+  c.s_begin = s_begin; c.s_end = s_end;
+  return dispatch_steps(c, mode, st);
+}
+
 int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
                   const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, float lr, float reg,
                   float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, int64_t ws_bytes, float* stats,
@@ -639,54 +1015,64 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  StepCtx c;
-  c.P = P; c.Q = Q; c.accP = accP; c.accQ = accQ; c.u = u; c.i = i; c.j = j;
-  c.d = d; c.B = B; c.S = S;
-  c.lr = lr;
-  // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
-  c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
-  c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
-  c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt);
-  c.useg_user = at<int32_t>(ws, L.off_useg_user); c.useg_off = at<int32_t>(ws, L.off_useg_off);
-  c.strip = at<int32_t>(ws, L.off_strip); c.slot_i = at<int32_t>(ws, L.off_slot_i); c.slot_j = at<int32_t>(ws, L.off_slot_j);
-  c.iu_item = at<int32_t>(ws, L.off_iu_item);
-  c.GQ = at<float>(ws, L.off_GQ); c.HQ = at<float>(ws, L.off_HQ); c.GP = at<float>(ws, L.off_GP);
-  c.cbuf = at<float>(ws, L.off_cbuf);
-  c.stats = stats;
   if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
-  return dispatch_steps(c, mode, st);
+  return run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, 0, S, st);
 }
 
+// prepare + run, software-pipelined: the index preparation of sub-chunk c+1 runs on its own stream while the step
+// kernels of sub-chunk c run on the caller's stream (prepare touches only its hash tables and the per-step arrays of its
+// own steps; the step kernels touch only the embedding tables, the gradient workspace and their own steps' arrays).
 int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
                     const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, float lr, float reg,
                     float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, int64_t ws_bytes, float* stats,
                     apr_stream_t stream) {
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws);
   if (rc) return rc;
-  rc = prepare_impl(u, i, j, S, B, d, rows_p, rows_q, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  if (mode != 0 && mode != 1) return APR_E_ARG;
+  const TrainLayout L = make_layout(S, B, d);
+  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AuxStream& ax = aux_stream();
+  if (!ax.ok) return APR_E_CUDA;
+  if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
+  // everything already enqueued on the caller's stream (producers of u,i,j; earlier steps reading the arrays) first
+  APR_CUDA_CHECK(cudaEventRecord(ax.entry, st));
+  APR_CUDA_CHECK(cudaStreamWaitEvent(ax.prep_stream, ax.entry, 0));
+  rc = prepare_clear(L, ws, ax.prep_stream);
   if (rc) return rc;
-  return apr_train_run(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, lr, reg, reg_adv, eps, adver, mode, ws, ws_bytes,
-                       stats, stream);
+  const int nsub = (S + L.Sc - 1) / L.Sc;
+  for (int k = 0; k < nsub; ++k) {
+    const int s0 = k * L.Sc, ns = std::min(L.Sc, S - s0);
+    rc = prepare_sub(u, i, j, L, s0, ns, rows_p, rows_q, ws, ax.prep_stream);
+    if (rc) return rc;
+    cudaEvent_t e = ax.prep_event(size_t(k));
+    if (!e) return APR_E_CUDA;
+    APR_CUDA_CHECK(cudaEventRecord(e, ax.prep_stream));
+  }
+  for (int k = 0; k < nsub; ++k) {
+    const int s0 = k * L.Sc, ns = std::min(L.Sc, S - s0);
+    APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.prep_event(size_t(k)), 0));
+    rc = run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, s0, s0 + ns, st);
+    if (rc) return rc;
+  }
+  return APR_OK;
 }
 
 int apr_train_unique_counts(const void* ws, int32_t S, int32_t B, int32_t d, int32_t* counts_host, apr_stream_t stream) {
   if (!ws || !counts_host || S < 1 || B < 1 || !valid_dim(d)) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int32_t* tmp = static_cast<int32_t*>(malloc(size_t(S) * 8));
+  int32_t* tmp = static_cast<int32_t*>(malloc(size_t(S) * 8 + 8));
   if (!tmp) return APR_E_ARG;
-  cudaError_t e = cudaMemcpyAsync(tmp, static_cast<const char*>(ws) + L.off_ucnt, size_t(S) * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(tmp + S, static_cast<const char*>(ws) + L.off_icnt, size_t(S) * 4, cudaMemcpyDeviceToHost, st);
+  const char* base = static_cast<const char*>(ws);
+  cudaError_t e = cudaMemcpyAsync(tmp, base + L.off_ucnt, size_t(S) * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + S, base + L.off_iall, size_t(S) * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp + 2 * S, base + L.off_hdr, 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { free(tmp); set_cuda_error(e, "apr_train_unique_counts"); return APR_E_CUDA; }
   for (int s = 0; s < S; ++s) { counts_host[2 * s] = tmp[s]; counts_host[2 * s + 1] = tmp[S + s]; }
-  // id-range flag
-  int32_t flag = 0;
-  e = cudaMemcpyAsync(&flag, static_cast<const char*>(ws) + L.off_hdr, 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  const int32_t flag = tmp[2 * S];
   free(tmp);
-  if (e != cudaSuccess) { set_cuda_error(e, "apr_train_unique_counts"); return APR_E_CUDA; }
   return flag ? APR_E_ARG : APR_OK;
 }
 

@@ -29,10 +29,10 @@ CFG = {"users": 10_000_000, "items": 2_000_000, "d": 128, "eps": 0.5, "reg_adv":
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4096)
-    ap.add_argument("--warmup", type=int, default=256)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("APR_BENCH_BATCH", "16384")))
-    ap.add_argument("--mode", type=int, default=int(os.environ.get("APR_BENCH_MODE", "1")))
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("APR_BENCH_BATCH", "65536")))
+    ap.add_argument("--mode", type=int, default=int(os.environ.get("APR_BENCH_MODE", "0")))
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--users", type=int, default=CFG["users"])
     ap.add_argument("--items", type=int, default=CFG["items"])
@@ -164,7 +164,7 @@ def workload_config(args):
     return {"workload": "BASELINE.json configs[3]: synthetic %dM users x %dM items, d=%d, APR step (eps 0.5, reg_adv 1, "
                         "lr 0.05, Adagrad), uniform triples" % (args.users // 10 ** 6, args.items // 10 ** 6, args.dim),
             "users": args.users, "items": args.items, "d": args.dim, "batch_per_step": args.batch,
-            "step_mode": "persistent-cooperative" if args.mode == 1 else "kernel-per-phase",
+            "step_mode": "persistent-cooperative" if args.mode == 1 else "fast-kernel || general-stages (2 streams)",
             "cache": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" %
                      (2 * 4 * args.dim * (args.users + args.items) / 1e9)}
 
@@ -252,7 +252,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * K * B / (ms * 1e-3)
-    launches = sum(4 + (1 if args.mode == 1 else 3 * c[0].shape[0]) for c in chunks)
+    def n_launches(S):  # 5 index-preparation kernels per L2-sized sub-chunk + the step kernels (csrc/train.cu)
+        p2 = 1 << max(0, (B - 1).bit_length())
+        sc = max(1, min(S, (48 << 20) // ((max(32, 2 * p2) + max(32, 4 * p2)) * 8)))
+        return 4 * -(-S // sc) + (1 if args.mode == 1 else 4 * S)
+    launches = sum(n_launches(c[0].shape[0]) for c in chunks)
 
     # ---- roofline of the dominant kernel(s): the embedding step kernels, index preparation excluded -------
     # algorithmic bytes per step = 16 d (U_uniq + I_uniq) + 12 B   
@@ -273,7 +277,7 @@ def main():
     steps_roof = sum(c[0].shape[0] for c in chunks[:n_roof])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_kind": peak_kind,
-                "kernel": "step_persistent_kernel<32,1>" if args.mode == 1 else "step_phase_kernel<32,1,{1,2,3}>",
+                "kernel": "step_persistent_kernel<32,1,true>" if args.mode == 1 else "fast_kernel<32,1,true> || 3 x general_stage_kernel<32,1> per step",
                 "bytes_per_step_model": bytes_total / steps_roof, "ms_per_step_kernel": ms_run / steps_roof}
 
     # ---- e2e: public API with HOST batches; H2D of ids and D2H of the per-step loss inside the region ------
