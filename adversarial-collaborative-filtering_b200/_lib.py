@@ -75,6 +75,12 @@ _SIGNATURES = {
     "apr_train_prepare": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int64, c_int64, _P, c_int64, _P]),
     "apr_train_run": (ctypes.c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, c_int32, c_float,
                                      c_float, c_float, c_float, c_int32, c_int32, _P, c_int64, _P, _P]),
+    "apr_train_layout": (ctypes.c_int, [c_int32, c_int32, c_int32, POINTER(c_int64)]),
+    "apr_train_prepare_range": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int64, c_int64, _P, c_int64,
+                                               c_int32, c_int32, c_int32, _P]),
+    "apr_train_stage_sharded": (ctypes.c_int, [POINTER(c_void_p)] * 6 + [c_int32, c_int32, c_int32, c_int32, c_int32,
+                                               c_float, c_float, c_float, c_float, c_int32, _P, c_int64, _P, c_int32,
+                                               c_int32, _P]),
     "apr_train_unique_counts": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
     "apr_loss_acc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]),
     "apr_score_pairs": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P]),

@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -261,18 +262,34 @@ __global__ void prep_pack_kernel(int s0, int ns, int B, const int32_t* __restric
 // ------------------------------------------------------------------------------------------------
 // step kernels
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+// Tables are row-sharded: row r lives on rank r & (nranks-1) at local row r >> rshift (nranks a power of two; 1 on a
+// single GPU).  Pb/Qb/... hold every rank's shard base (peer-mapped over NVLink); G_Q/H_Q slots are sharded the same way.
 struct StepCtx {
-  float* P; float* Q; float* accP; float* accQ;
+  float* Pb[kMaxRanks]; float* Qb[kMaxRanks]; float* aPb[kMaxRanks]; float* aQb[kMaxRanks];
+  float* GQb[kMaxRanks]; float* HQb[kMaxRanks];
+  int nranks, rank, rshift;
   int d, B, S;
   float lr, kreg, reg_adv, eps;
   int adver;
   const int32_t* ucnt; const int32_t* icnt; const int32_t* nslow;
   const int4* seg_hdr; const int4* rec; const int32_t* iu_item;
-  float* GQ; float* HQ; float* GP; float* cbuf;
+  float* GP; float* cbuf;
   float* stats;  // nullable [S,2]
   int flags;     // tuning switches (APR_STEP_FLAGS)
   int s_begin, s_end;  // steps of this launch
+  int only_stage;      // -1: whole step; 0,1,2: that general stage; 3: fast kernel (sharded driver, one launch per call)
 };
+
+__device__ __forceinline__ float* shard_row(float* const* base, int id, int d, const StepCtx& c) {
+  return base[id & (c.nranks - 1)] + int64_t(id >> c.rshift) * d;
+}
+#define P_ROW(c, id) shard_row((c).Pb, (id), (c).d, (c))
+#define Q_ROW(c, id) shard_row((c).Qb, (id), (c).d, (c))
+#define AP_ROW(c, id) shard_row((c).aPb, (id), (c).d, (c))
+#define AQ_ROW(c, id) shard_row((c).aQb, (id), (c).d, (c))
+#define GQ_ROW(c, slot) shard_row((c).GQb, (slot), (c).d, (c))
+#define HQ_ROW(c, slot) shard_row((c).HQb, (slot), (c).d, (c))
 
 template <int G, int V>
 struct Row {
@@ -387,8 +404,8 @@ __device__ __forceinline__ void stats_flush(float* stats, int s, float loss, flo
 template <int G, int V>
 __device__ __forceinline__ void item_sink(const StepCtx& c, int item, int slot, const Row<G, V>& w, const Row<G, V>& g,
                                           int lane, int d) {
-  if (slot >= 0) row_red<G, V>(g, c.HQ + int64_t(slot) * d, lane, d);
-  else adagrad_row<G, V>(c.Q + int64_t(item) * d, c.accQ + int64_t(item) * d, w, g, lane, d, c.lr);
+  if (slot >= 0) row_red<G, V>(g, HQ_ROW(c, slot), lane, d);
+  else adagrad_row<G, V>(Q_ROW(c, item), AQ_ROW(c, item), w, g, lane, d, c.lr);
 }
 
 // adversarial forward/backward of one triple given the plain coefficient cf and the row gradients gi, gj of its items
@@ -398,12 +415,12 @@ __device__ __forceinline__ void adv_triple(const StepCtx& c, const int4 rc, floa
                                            const Row<G, V>& pd, const Row<G, V>& q, const Row<G, V>& n, Row<G, V>& g,
                                            int lane, int d, unsigned mask) {
   Row<G, V> gi, gj;
-  if (rc.z >= 0) row_load<G, V>(gi, c.GQ + int64_t(rc.z) * d, lane, d);
+  if (rc.z >= 0) row_load<G, V>(gi, GQ_ROW(c, rc.z), lane, d);
   else {
 #pragma unroll
     for (int k = 0; k < V; ++k) gi.v[k] = f4_scale(p.v[k], cf);
   }
-  if (rc.w >= 0) row_load<G, V>(gj, c.GQ + int64_t(rc.w) * d, lane, d);
+  if (rc.w >= 0) row_load<G, V>(gj, GQ_ROW(c, rc.w), lane, d);
   else {
 #pragma unroll
     for (int k = 0; k < V; ++k) gj.v[k] = f4_scale(p.v[k], -cf);
@@ -448,12 +465,12 @@ template <int G, int V, bool FULL>
 __device__ __forceinline__ void fast_segment(const StepCtx& c, const int user, const int item_i, const int item_j, int lane,
                                              unsigned mask, StepStats& st) {
   const int d = c.d;
-  float* Pu = c.P + int64_t(user) * d;
-  float* Au = c.accP + int64_t(user) * d;
-  float* Qi = c.Q + int64_t(item_i) * d;
-  float* Ai = c.accQ + int64_t(item_i) * d;
-  float* Qj = c.Q + int64_t(item_j) * d;
-  float* Aj = c.accQ + int64_t(item_j) * d;
+  float* Pu = P_ROW(c, user);
+  float* Au = AP_ROW(c, user);
+  float* Qi = Q_ROW(c, item_i);
+  float* Ai = AQ_ROW(c, item_i);
+  float* Qj = Q_ROW(c, item_j);
+  float* Aj = AQ_ROW(c, item_j);
   float4 p[V], q[V], n[V], ap[V], ai[V], aj[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
@@ -527,7 +544,7 @@ template <int G, int V, bool FULL>
 __device__ __forceinline__ void fast_range(const StepCtx& c, int s, int k0, int k1, int gid, int ngroups, int lane,
                                            unsigned mask, StepStats& st) {
   const int4* seg_hdr = c.seg_hdr + int64_t(s) * c.B * 2;
-  for (int k = k0 + gid; k < k1; k += ngroups) {
+  for (int k = k0 + gid * c.nranks + c.rank; k < k1; k += ngroups * c.nranks) {
     const int user = __ldg(&seg_hdr[2 * k].x);
     const int2 ij = __ldg(reinterpret_cast<const int2*>(&seg_hdr[2 * k + 1]));
     fast_segment<G, V, FULL>(c, user, ij.x, ij.y, lane, mask, st);
@@ -546,8 +563,8 @@ __device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0
   const bool adver = c.adver != 0;
   const int user = h0.x;
   const int b0 = h0.y, b1 = h0.y + h0.z;
-  float* Pu = c.P + int64_t(user) * d;
-  float* Au = c.accP + int64_t(user) * d;
+  float* Pu = P_ROW(c, user);
+  float* Au = AP_ROW(c, user);
   Row<G, V> p, g;
   row_load<G, V>(p, Pu, lane, d);
   row_zero<G, V>(g);
@@ -555,8 +572,8 @@ __device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0
   for (int pos = b0; pos < b1; ++pos) {
     if (pos > b0) rc = rec[pos];
     Row<G, V> q, n;
-    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
-    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
+    row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
     const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
     float r;
     const float cf = bpr_coeff(x, r);
@@ -585,8 +602,8 @@ __device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0
     for (int pos = b0; pos < b1; ++pos) {
       if (pos > b0) rc = rec[pos];
       Row<G, V> q, n;
-      row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
-      row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+      row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
+      row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
       const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
       float r;
       const float cf = bpr_coeff(x, r);
@@ -603,14 +620,14 @@ __device__ __forceinline__ void slow_plain(const StepCtx& c, int k0, const int4 
   const int d = c.d;
   const int b0 = h0.y, b1 = h0.y + h0.z;
   Row<G, V> p, g;
-  row_load<G, V>(p, c.P + int64_t(h0.x) * d, lane, d);
+  row_load<G, V>(p, P_ROW(c, h0.x), lane, d);
   row_zero<G, V>(g);
   int4 rc = h1;
   for (int pos = b0; pos < b1; ++pos) {
     if (pos > b0) rc = rec[pos];
     Row<G, V> q, n;
-    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
-    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
+    row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
     const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
     float r;
     const float cf = bpr_coeff(x, r);
@@ -618,11 +635,11 @@ __device__ __forceinline__ void slow_plain(const StepCtx& c, int k0, const int4 
     Row<G, V> t;
 #pragma unroll
     for (int k = 0; k < V; ++k) { g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]); t.v[k] = f4_scale(p.v[k], cf); }
-    if (rc.z >= 0) row_red<G, V>(t, c.GQ + int64_t(rc.z) * d, lane, d);
+    if (rc.z >= 0) row_red<G, V>(t, GQ_ROW(c, rc.z), lane, d);
     if (rc.w >= 0) {
 #pragma unroll
       for (int k = 0; k < V; ++k) t.v[k] = f4_scale(t.v[k], -1.f);
-      row_red<G, V>(t, c.GQ + int64_t(rc.w) * d, lane, d);
+      row_red<G, V>(t, GQ_ROW(c, rc.w), lane, d);
     }
     if (lane == 0) c.cbuf[pos] = cf;
   }
@@ -638,7 +655,7 @@ __device__ __forceinline__ void slow_adv(const StepCtx& c, int k0, const int4 h0
   const int b0 = h0.y, b1 = h0.y + h0.z;
   int4 rc = h1;
   Row<G, V> p, g, pd;
-  row_load<G, V>(p, c.P + int64_t(h0.x) * d, lane, d);
+  row_load<G, V>(p, P_ROW(c, h0.x), lane, d);
   row_load<G, V>(g, c.GP + int64_t(k0) * d, lane, d);
   const float sp = delta_scale<G, V>(g, c.eps, mask);
 #pragma unroll
@@ -647,11 +664,11 @@ __device__ __forceinline__ void slow_adv(const StepCtx& c, int k0, const int4 h0
     if (pos > b0) rc = rec[pos];
     const float cf = __ldcg(&c.cbuf[pos]);
     Row<G, V> q, n;
-    row_load<G, V>(q, c.Q + int64_t(rc.x) * d, lane, d);
-    row_load<G, V>(n, c.Q + int64_t(rc.y) * d, lane, d);
+    row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
+    row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
     adv_triple<G, V>(c, rc, cf, p, pd, q, n, g, lane, d, mask);
   }
-  adagrad_row<G, V>(c.P + int64_t(h0.x) * d, c.accP + int64_t(h0.x) * d, p, g, lane, d, c.lr);
+  adagrad_row<G, V>(P_ROW(c, h0.x), AP_ROW(c, h0.x), p, g, lane, d, c.lr);
 }
 
 // stage 2: shared item slots
@@ -662,15 +679,15 @@ __device__ __forceinline__ void items_shared(const StepCtx& c, int s, int gid, i
   const int32_t* iu_item = c.iu_item + int64_t(s) * B;
   Row<G, V> z;
   row_zero<G, V>(z);
-  for (int slot = gid; slot < ni; slot += ngroups) {
+  for (int slot = gid * c.nranks + c.rank; slot < ni; slot += ngroups * c.nranks) {
     const int item = iu_item[slot];
     Row<G, V> w, g, a;
-    row_load<G, V>(g, c.HQ + int64_t(slot) * d, lane, d);
-    row_load<G, V>(w, c.Q + int64_t(item) * d, lane, d);
-    row_load<G, V>(a, c.accQ + int64_t(item) * d, lane, d);
-    adagrad_apply<G, V>(c.Q + int64_t(item) * d, c.accQ + int64_t(item) * d, w, a, g, lane, d, c.lr);
-    row_store<G, V>(z, c.HQ + int64_t(slot) * d, lane, d);
-    if (c.adver) row_store<G, V>(z, c.GQ + int64_t(slot) * d, lane, d);
+    row_load<G, V>(g, HQ_ROW(c, slot), lane, d);
+    row_load<G, V>(w, Q_ROW(c, item), lane, d);
+    row_load<G, V>(a, AQ_ROW(c, item), lane, d);
+    adagrad_apply<G, V>(Q_ROW(c, item), AQ_ROW(c, item), w, a, g, lane, d, c.lr);
+    row_store<G, V>(z, HQ_ROW(c, slot), lane, d);
+    if (c.adver) row_store<G, V>(z, GQ_ROW(c, slot), lane, d);
   }
 }
 
@@ -686,7 +703,7 @@ __device__ __forceinline__ void general_stage(const StepCtx& c, int s, int stage
   const int ng = c.nslow[s];
   const int4* seg_hdr = c.seg_hdr + int64_t(s) * B * 2;
   const int4* rec = c.rec + int64_t(s) * B;
-  for (int k0 = gid; k0 < ng; k0 += ngroups) {
+  for (int k0 = gid * c.nranks + c.rank; k0 < ng; k0 += ngroups * c.nranks) {
     const int4 h0 = __ldg(&seg_hdr[2 * k0]);
     const int4 h1 = __ldg(&seg_hdr[2 * k0 + 1]);
     const bool shared = h0.w != 0;
@@ -808,6 +825,14 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
     const int gb = gen_bps > 0 ? gen_bps : 2;
     const int grid_fast = std::max(1, std::min((c.B + gpb - 1) / gpb, sms * fb));
     const int grid_gen = std::max(1, std::min((c.B + gpb - 1) / gpb, sms * gb));
+    if (c.only_stage >= 0) {
+      for (int s = c.s_begin; s < c.s_end; ++s) {
+        if (c.only_stage == 3) fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, st>>>(c, s);
+        else if (c.only_stage > 0 || c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, c.only_stage);
+      }
+      APR_LAUNCH_CHECK();
+      return APR_OK;
+    }
     for (int s = c.s_begin; s < c.s_end; ++s) {
       APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
       APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
@@ -939,6 +964,14 @@ static int prepare_clear(const TrainLayout& L, void* ws, cudaStream_t st) {
   return APR_OK;
 }
 
+// the same for the steps [s0, s0+ns) only (other steps' arrays may already hold another rank's broadcast)
+static int prepare_clear_range(const TrainLayout& L, void* ws, int s0, int ns, cudaStream_t st) {
+  const int64_t offs[6] = {L.off_ucnt, L.off_icnt, L.off_iall, L.off_nslow, L.off_nfast, L.off_tcursor};
+  for (int k = 0; k < 6; ++k) APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, offs[k]) + int64_t(s0) * 4, 0, size_t(ns) * 4, st));
+  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_seg_slow) + int64_t(s0) * L.B * 4, 0, size_t(ns) * L.B * 4, st));
+  return APR_OK;
+}
+
 static int prepare_impl(const int32_t* u, const int32_t* i, const int32_t* j, int S, int B, int d, int64_t rows_p,
                         int64_t rows_q, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const TrainLayout L = make_layout(S, B, d);
@@ -986,7 +1019,10 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
                      float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, const TrainLayout& L, float* stats,
                      int s_begin, int s_end, cudaStream_t st) {
   StepCtx c;
-  c.P = P; c.Q = Q; c.accP = accP; c.accQ = accQ;
+  memset(&c, 0, sizeof(c));
+  c.Pb[0] = P; c.Qb[0] = Q; c.aPb[0] = accP; c.aQb[0] = accQ;
+  c.GQb[0] = at<float>(ws, L.off_GQ); c.HQb[0] = at<float>(ws, L.off_HQ);
+  c.nranks = 1; c.rank = 0; c.rshift = 0; c.only_stage = -1;
   c.d = d; c.B = B; c.S = S;
   c.lr = lr;
   // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
@@ -997,7 +1033,7 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr);
   c.rec = at<int4>(ws, L.off_rec);
   c.iu_item = at<int32_t>(ws, L.off_iu_item);
-  c.GQ = at<float>(ws, L.off_GQ); c.HQ = at<float>(ws, L.off_HQ); c.GP = at<float>(ws, L.off_GP);
+  c.GP = at<float>(ws, L.off_GP);
   c.cbuf = at<float>(ws, L.off_cbuf);
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
@@ -1056,6 +1092,61 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
     if (rc) return rc;
   }
   return APR_OK;
+}
+
+int apr_train_layout(int32_t S, int32_t B, int32_t d, int64_t* out) {
+  if (!out || S < 1 || B < 1 || !valid_dim(d)) return APR_E_ARG;
+  const TrainLayout L = make_layout(S, B, d);
+  out[0] = L.total; out[1] = L.Sc; out[2] = L.off_ucnt; out[3] = L.off_icnt; out[4] = L.off_iall; out[5] = L.off_nslow;
+  out[6] = L.off_seg_hdr; out[7] = L.off_rec; out[8] = L.off_iu_item; out[9] = L.off_hdr;
+  return APR_OK;
+}
+
+int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, int32_t d,
+                            int64_t rows_p, int64_t rows_q, void* ws, int64_t ws_bytes, int32_t s0, int32_t ns,
+                            int32_t clear_counters, apr_stream_t stream) {
+  if (!u || !i || !j || !ws || S < 1 || B < 1 || rows_p < 1 || rows_q < 1 || !valid_dim(d)) return APR_E_ARG;
+  if (s0 < 0 || ns < 1 || s0 + ns > S) return APR_E_ARG;
+  if (!aligned16(ws)) return APR_E_ALIGN;
+  const TrainLayout L = make_layout(S, B, d);
+  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = clear_counters ? prepare_clear_range(L, ws, s0, ns, st) : APR_OK;
+  for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st);
+  return rc;
+}
+
+int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                            float* const* GQb, float* const* HQb, int32_t nranks, int32_t rank, int32_t d, int32_t S,
+                            int32_t B, float lr, float reg, float reg_adv, float eps, int32_t adver, void* ws,
+                            int64_t ws_bytes, float* stats, int32_t step, int32_t stage, apr_stream_t stream) {
+  if (!Pb || !Qb || !accPb || !accQb || !GQb || !HQb || !ws) return APR_E_ARG;
+  if (nranks < 1 || nranks > kMaxRanks || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return APR_E_ARG;
+  if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 3) return APR_E_ARG;
+  const TrainLayout L = make_layout(S, B, d);
+  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  StepCtx c;
+  memset(&c, 0, sizeof(c));
+  for (int r = 0; r < nranks; ++r) {
+    if (!Pb[r] || !Qb[r] || !accPb[r] || !accQb[r] || !GQb[r] || !HQb[r]) return APR_E_ARG;
+    if (!aligned16(Pb[r]) || !aligned16(Qb[r]) || !aligned16(accPb[r]) || !aligned16(accQb[r]) || !aligned16(GQb[r]) ||
+        !aligned16(HQb[r]))
+      return APR_E_ALIGN;
+    c.Pb[r] = Pb[r]; c.Qb[r] = Qb[r]; c.aPb[r] = accPb[r]; c.aQb[r] = accQb[r]; c.GQb[r] = GQb[r]; c.HQb[r] = HQb[r];
+  }
+  c.nranks = nranks; c.rank = rank;
+  c.rshift = 0;
+  while ((1 << c.rshift) < nranks) ++c.rshift;
+  c.d = d; c.B = B; c.S = S; c.lr = lr;
+  c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
+  c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
+  c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt); c.nslow = at<int32_t>(ws, L.off_nslow);
+  c.seg_hdr = at<int4>(ws, L.off_seg_hdr); c.rec = at<int4>(ws, L.off_rec); c.iu_item = at<int32_t>(ws, L.off_iu_item);
+  c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf);
+  c.stats = stats;
+  c.flags = 0;
+  c.s_begin = step; c.s_end = step + 1; c.only_stage = stage;
+  return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream));
 }
 
 int apr_train_unique_counts(const void* ws, int32_t S, int32_t B, int32_t d, int32_t* counts_host, apr_stream_t stream) {

@@ -138,6 +138,40 @@ def train_run(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: Train
     _lib.check(_lib.lib().apr_train_run(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
 
 
+def train_layout(n_steps: int, batch: int, d: int) -> dict:
+    """Byte offsets of the index arrays inside a TrainWorkspace (for the sharded driver's broadcasts)."""
+    out = (ctypes.c_int64 * 10)()
+    _lib.check(_lib.lib().apr_train_layout(n_steps, batch, d, out))
+    keys = ["total", "Sc", "ucnt", "icnt", "iall", "nslow", "seg_hdr", "rec", "iu_item", "hdr"]
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def train_prepare_range(rows_p: int, rows_q: int, u, i, j, ws: "TrainWorkspace", s0: int, ns: int, clear: bool = True) -> None:
+    S, B = u.shape
+    _lib.check(_lib.lib().apr_train_prepare_range(_ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), S, B,
+                                                  ws.d, rows_p, rows_q, ws.buf.data_ptr(), ws.nbytes, s0, ns, int(clear),
+                                                  _stream()))
+
+
+def _ptr_array(ptrs):
+    arr = (ctypes.c_void_p * len(ptrs))()
+    for k, p in enumerate(ptrs):
+        arr[k] = int(p)
+    return arr
+
+
+def train_stage_sharded(ptrs: dict, nranks: int, rank: int, d: int, n_steps: int, batch: int, lr, reg, reg_adv, eps, adver,
+                        ws: "TrainWorkspace", step: int, stage: int, stats: Optional[torch.Tensor] = None) -> None:
+    """One stage of one step on row-sharded tables.  ``ptrs`` maps P,Q,accP,accQ,GQ,HQ to lists of nranks shard base
+    pointers (ints).  stage 0,1,2 = general path, 3 = fast kernel."""
+    a = ptrs.get("_c")
+    if a is None:
+        a = ptrs["_c"] = [_ptr_array(ptrs[k]) for k in ("P", "Q", "accP", "accQ", "GQ", "HQ")]
+    _lib.check(_lib.lib().apr_train_stage_sharded(*a, nranks, rank, d, n_steps, batch, float(lr), float(reg), float(reg_adv),
+                                                  float(eps), int(bool(adver)), ws.buf.data_ptr(), ws.nbytes,
+                                                  _ptr(stats, torch.float32), step, stage, _stream()))
+
+
 def loss_acc(P, Q, u, i, j) -> torch.Tensor:
     """-> float64 [S,2]: per batch {sum softplus(-r), count(x>0)} (utils.py:159-175)."""
     S, B = u.shape

@@ -173,7 +173,129 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        return main_sharded(args)
+    return main_single(args)
 
+
+def main_sharded(args):
+    """N > 1: the same tables row-sharded over the N GPUs (BASELINE.json configs[3] verbatim), weak scaling: every rank
+    contributes args.batch triples to each step, so the global batch is N * batch."""
+    import torch
+    import torch.distributed as dist
+
+    from apr_b200 import engine
+    from apr_b200.distributed import ShardedTables, train_steps_sharded
+
+    world = int(os.environ["WORLD_SIZE"])
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    U, I, d, Bl, K, W = args.users, args.items, args.dim, args.batch, max(1, args.steps), max(3, args.warmup)
+    Bg = Bl * world
+    hbm_peak, _, peak_kind = peaks()
+    t = ShardedTables(U, I, d, Bg, dev, world=world, rank=rank, symmetric=True)
+    engine.init_truncated_normal(t.local("P"), 0.01, 2019, 2 * rank)
+    engine.init_truncated_normal(t.local("Q"), 0.01, 2019, 2 * rank + 1)
+    engine.fill(t.local("accP"), 0.1)
+    engine.fill(t.local("accQ"), 0.1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    rng = np.random.default_rng(2019 + rank)
+    CH = max(1, min(64, (1 << 22) // Bg))
+    ws = engine.TrainWorkspace(CH, Bg, d, dev)
+    aux = torch.cuda.Stream()
+    hp = (CFG["lr"], CFG["reg"], CFG["reg_adv"], CFG["eps"], 1)
+
+    def global_chunk(n, host=None):
+        """local triples [n, Bl] -> all_gather -> global [n, Bg] on every rank"""
+        loc = host if host is not None else synth_triples(rng, n, Bl, U, I)
+        outs = []
+        for x in loc:
+            xl = (torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) if host is not None
+                  else torch.from_numpy(x).to(dev))
+            g = torch.empty((world, n, Bl), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(g, xl.contiguous())
+            outs.append(g.permute(1, 0, 2).reshape(n, Bg).contiguous())
+        return outs
+
+    def run_chunk(u, i, j, stats=None):
+        train_steps_sharded(t, u, i, j, *hp, ws, aux_stream=aux, stats=stats)
+
+    done = 0
+    while done < W:
+        n = min(CH, W - done)
+        run_chunk(*global_chunk(n))
+        done += n
+    chunks, left = [], K
+    while left > 0:
+        n = min(CH, left)
+        chunks.append(global_chunk(n))
+        left -= n
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for c in chunks:
+        run_chunk(*c)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = K * Bg / (ms * 1e-3)
+    # algorithmic bytes of the global steps (same index arrays on every rank)
+    cnt = ws.unique_counts(chunks[-1][0].shape[0]).astype(np.int64)
+    bytes_step = float(16 * d * cnt.sum() + 12 * Bg * cnt.shape[0]) / cnt.shape[0]
+    achieved = bytes_step * K / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak * world, "unit": "GB/s",
+                "frac": achieved / (hbm_peak * world), "traffic": None, "peak_kind": peak_kind,
+                "kernel": "fast_kernel + general_stage_kernel over NVLink-peer-mapped row shards",
+                "note": "aggregate over %d GPUs; (G-1)/G of the row traffic crosses NVLink (770 GB/s/dir/GPU measured)" % world}
+    # e2e: host batches on every rank -> H2D -> all_gather -> sharded steps -> D2H of the per-step loss
+    Ke = min(K, CH)
+    host = synth_triples(rng, Ke, Bl, U, I)
+    stats = torch.zeros((Ke, 2), dtype=torch.float32, device=dev)
+
+    def e2e_pass():
+        g = global_chunk(Ke, host=host)
+        stats.zero_()
+        run_chunk(*g, stats=stats)
+        dist.all_reduce(stats)
+        return stats.cpu()
+
+    e2e_pass()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_pass()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": Ke * Bg / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": 12 * Bl, "d2h_bytes_per_step": 8,
+           "steps": Ke, "api": "distributed.train_steps_sharded(host batches per rank)"}
+    cfgd = workload_config(args)
+    cfgd.update({"batch_per_step": Bg, "batch_per_gpu": Bl, "parallelism": "row-sharded tables over %d GPUs (NVLink peer "
+                 "loads/stores/REDs inside the kernels), data-parallel over triples" % world,
+                 "step_mode": "fast-kernel || general-stages, 3 cross-rank barriers per step"})
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfgd, "roofline": roofline, "e2e": e2e, "gpu_launches": K * 4 + 4 * len(chunks), "clocks": clocks}
+    if rank == 0:
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def main_single(args):
     import torch
     import torch.distributed as dist
 
@@ -181,13 +303,11 @@ def main():
     from apr_b200.APR import MF, Session
     from apr_b200.utils import training_batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    world = 1
+    rank = 0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = engine.require_cuda()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     U, I, d, B, K, W = args.users, args.items, args.dim, args.batch, max(1, args.steps), max(3, args.warmup)
     hbm_peak, tc_peak, peak_kind = peaks()

@@ -98,6 +98,24 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
 int apr_train_unique_counts(const void* workspace, int32_t n_steps, int32_t batch, int32_t d, int32_t* counts_host,
                             apr_stream_t stream);
 
+/* ---- Row-sharded training over peer-mapped tables (multi-GPU drop-in for the same sess.run pair).
+ *      Row r of a table lives on rank r % nranks at local row r / nranks (nranks in {1,2,4,8}); Pb/Qb/accPb/accQb are
+ *      HOST arrays of nranks device pointers (each rank's shard base, peer-mapped over NVLink), GQb/HQb the shards of
+ *      the shared-item workspace (>= batch/nranks + 1 rows each, zeroed once).  `batch` is the GLOBAL batch; every rank
+ *      holds identical index arrays in `workspace` (apr_train_prepare_range on one rank + a broadcast of the regions
+ *      apr_train_layout reports) and processes every nranks-th segment.  One call launches ONE stage of ONE step:
+ *      stage 0,1,2 = general path, 3 = fast kernel; the caller puts a cross-rank barrier after stages 0, 1 and
+ *      after {2,3}.  apr_b200/distributed.py is that caller. */
+int apr_train_layout(int32_t n_steps, int32_t batch, int32_t d, int64_t* out10);
+int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch,
+                            int32_t d, int64_t rows_p, int64_t rows_q, void* workspace, int64_t workspace_bytes,
+                            int32_t first_step, int32_t count, int32_t clear_counters, apr_stream_t stream);
+int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                            float* const* GQb, float* const* HQb, int32_t nranks, int32_t rank, int32_t d,
+                            int32_t n_steps, int32_t batch, float lr, float reg, float reg_adv, float eps, int32_t adver,
+                            void* workspace, int64_t workspace_bytes, float* stats, int32_t step, int32_t stage,
+                            apr_stream_t stream);
+
 /* ---- A9 / K7: training_loss_acc, utils.py:159-175 (output_adv = 0): per batch s,
  *      out[2s] = sum_b softplus(-clip(x_b)), out[2s+1] = count(x_b > 0), as float64. */
 int apr_loss_acc(const float* P, const float* Q, int32_t d, const int32_t* u, const int32_t* i, const int32_t* j,

@@ -1,0 +1,115 @@
+"""Real multi-GPU runs (need >= 2 GPUs on the box; skipped otherwise): row-sharded training over peer-mapped tables and
+item-sharded evaluation, both compared with the oracle on rank 0."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import apr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _train_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from apr_b200 import engine
+    from apr_b200.distributed import ShardedTables, train_steps_sharded
+    rng = np.random.RandomState(7)
+    U, I, d, S, B = 3001, 1501, 64, 3, 2048
+    P = (rng.randn(U, d) * 0.1).astype(np.float32)
+    Q = (rng.randn(I, d) * 0.1).astype(np.float32)
+    u = rng.randint(0, U, (S, B)).astype(np.int32)
+    i = rng.randint(0, I, (S, B)).astype(np.int32)
+    j = rng.randint(0, I, (S, B)).astype(np.int32)
+    t = ShardedTables(U, I, d, B, dev, world=world, rank=rank, symmetric=True)
+    t.load_full("P", torch.from_numpy(P).to(dev))
+    t.load_full("Q", torch.from_numpy(Q).to(dev))
+    t.load_full("accP", torch.full((U, d), 0.1, device=dev))
+    t.load_full("accQ", torch.full((I, d), 0.1, device=dev))
+    torch.cuda.synchronize()
+    dist.barrier()
+    ws = engine.TrainWorkspace(S, B, d, dev)
+    aux = torch.cuda.Stream()
+    td = lambda a: torch.from_numpy(a).to(dev)
+    train_steps_sharded(t, td(u), td(i), td(j), 0.05, 0.01, 1.0, 0.5, 1, ws, aux_stream=aux)
+    torch.cuda.synchronize()
+    dist.barrier()
+    # every rank returns its shards; rank 0 reassembles and compares
+    parts = {n: t.local(n).cpu() for n in ("P", "Q", "accP", "accQ")}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, parts)
+    if rank == 0:
+        full = {}
+        for n, rows in (("P", U), ("Q", I), ("accP", U), ("accQ", I)):
+            a = np.zeros((rows, d), np.float32)
+            for r in range(world):
+                k = a[r::world].shape[0]
+                a[r::world] = gathered[r][n][:k].numpy()
+            full[n] = a
+        torch.save((full, P, Q, u, i, j), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_row_sharded_training_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    full, P, Q, u, i, j = torch.load(out, weights_only=False)
+    aP, aQ = np.full_like(P, 0.1), np.full_like(Q, 0.1)
+    for s in range(u.shape[0]):
+        O.apr_step(P, Q, aP, aQ, u[s], i[s], j[s], 0.05, 0.01, 1.0, 0.5, 1)
+    for got, ref in ((full["P"], P), (full["Q"], Q), (full["accP"], aP), (full["accQ"], aQ)):
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def _eval_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from apr_b200.Dataset import build_sorted_csr
+    from apr_b200.distributed import evaluate_item_sharded_cuda
+    rng = np.random.RandomState(3)
+    U, I, d = 200, 3000, 64
+    P = rng.randn(U, d).astype(np.float32)
+    Q = rng.randn(I + 1, d).astype(np.float32)
+    Q[17] = Q[2000]
+    train = [sorted(set(rng.randint(0, I, 9).tolist())) for _ in range(U)]
+    test = rng.randint(0, I, U).astype(np.int32)
+    ptr, idx = build_sorted_csr([train[k] + [int(test[k])] for k in range(U)])
+    td = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    pos, ids, sc = evaluate_item_sharded_cuda(td(P, torch.float32), td(Q, torch.float32), td(np.arange(U), torch.int32),
+                                              td(test, torch.int32), I, td(ptr, torch.int64), td(idx, torch.int32), k_top=10)
+    if rank == 0:
+        torch.save((pos.cpu(), ids.cpu(), P, Q, train, test, I), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_item_sharded_eval_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_eval_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    pos, ids, P, Q, train, test, I = torch.load(out, weights_only=False)
+    for u in range(P.shape[0]):
+        p, _, tids, _ = O.eval_fullrank_user(P, Q, u, int(test[u]), train[u], I, 10)
+        assert p == int(pos[u])
+        neg = [t for t in ids[u].tolist() if t >= 0]
+        merged = neg[:p] + [int(test[u])] + neg[p:] if p < 10 else neg
+        assert merged[:10] == tids.tolist()[:10]

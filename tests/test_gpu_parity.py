@@ -283,3 +283,33 @@ def test_eval_fullrank_item_sharded_sums(cuda_device):
     for lo, hi in ((0, 401), (401, 1000), (1000, I)):
         engine.eval_fullrank(*a, lo, hi, *e, 0, exact=True, position=acc)
     assert torch.equal(whole, acc)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("adver", [0, 1])
+def test_row_sharded_step_matches_oracle_emulated_ranks(cuda_device, world, adver):
+    """Row-sharded tables + every-G-th-segment work split (the multi-GPU training path) checked on ONE GPU: the G ranks'
+    stage launches run back to back (no launch waits on another), shards live in this device's memory."""
+    from apr_b200 import engine
+    from apr_b200.distributed import ShardedTables, train_steps_sharded
+    rng = np.random.RandomState(world * 10 + adver)
+    U, I, d, S, B = 3001, 1501, 64, 3, 1536
+    P, Q, u, i, j = _problem(rng, U, I, d, S, B)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 1.0, 0.5
+    rP, rQ, raP, raQ, _ = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, adver)
+    dev = cuda_device
+    t = ShardedTables(U, I, d, B, dev, world=world, rank=0, symmetric=False)
+    t.load_full("P", _dev(P, torch.float32, dev))
+    t.load_full("Q", _dev(Q, torch.float32, dev))
+    t.load_full("accP", torch.full((U, d), 0.1, device=dev))
+    t.load_full("accQ", torch.full((I, d), 0.1, device=dev))
+    ws = engine.TrainWorkspace(S, B, d, dev)
+    train_steps_sharded(t, _dev(u, torch.int32, dev), _dev(i, torch.int32, dev), _dev(j, torch.int32, dev), lr, reg, reg_adv,
+                        eps, adver, ws, ranks=list(range(world)))
+    torch.cuda.synchronize()
+    _close(t.gather_full("P", U).cpu().numpy(), rP)
+    _close(t.gather_full("Q", I).cpu().numpy(), rQ)
+    _close(t.gather_full("accP", U).cpu().numpy(), raP)
+    _close(t.gather_full("accQ", I).cpu().numpy(), raQ)
+    for r in range(world):  # shared-item workspace shards back to zero
+        assert int(t.local("GQ", r).count_nonzero().item()) == 0 and int(t.local("HQ", r).count_nonzero().item()) == 0
