@@ -81,6 +81,9 @@ _SIGNATURES = {
     "apr_train_stage_sharded": (ctypes.c_int, [POINTER(c_void_p)] * 6 + [c_int32, c_int32, c_int32, c_int32, c_int32,
                                                c_float, c_float, c_float, c_float, c_int32, _P, c_int64, _P, c_int32,
                                                c_int32, _P]),
+    "apr_train_steps_sharded": (ctypes.c_int, [POINTER(c_void_p)] * 7 + [c_int32, c_int32, c_int32, c_int32, c_int32,
+                                               c_float, c_float, c_float, c_float, c_int32, _P, c_int64, _P, c_int32,
+                                               c_int32, _P, _P]),
     "apr_train_unique_counts": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
     "apr_loss_acc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]),
     "apr_score_pairs": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P]),
@@ -88,6 +91,10 @@ _SIGNATURES = {
     "apr_eval_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "apr_eval_fullrank": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, _P, _P, _P,
                                          c_int32, _P, c_int64, _P]),
+    "apr_eval_tc_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "apr_eval_fullrank_tc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P,
+                                            _P]),
+    "apr_eval_tc_ambiguous": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
     "apr_sum_squares": (ctypes.c_int, [_P, c_int64, _P, _P]),
 }
 

@@ -330,6 +330,22 @@ int eval_fullrank_exact(const float* P, const float* Q, int d, const int32_t* us
   return APR_OK;
 }
 
+int launch_score_pairs(const float* P, const float* Q, int d, const int32_t* users, const int32_t* items, int64_t n,
+                       float* scores, cudaStream_t st) {
+  score_pairs_kernel<<<grid_for(n, 256), 256, 0, st>>>(P, Q, d, users, items, n, scores);
+  APR_LAUNCH_CHECK();
+  return APR_OK;
+}
+
+int launch_excl_correction(const float* P, const float* Q, int d, const int32_t* users, int n_users, const float* spos,
+                           int item_lo, int item_hi, const int64_t* excl_ptr, const int32_t* excl_idx, int32_t* position,
+                           cudaStream_t st) {
+  excl_correction_kernel<<<grid_for(int64_t(n_users) * 32, 256), 256, 0, st>>>(P, Q, d, users, n_users, spos, item_lo,
+                                                                               item_hi, excl_ptr, excl_idx, position);
+  APR_LAUNCH_CHECK();
+  return APR_OK;
+}
+
 }  // namespace apr
 
 using namespace apr;

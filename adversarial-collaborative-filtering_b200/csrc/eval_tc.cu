@@ -1,0 +1,432 @@
+// Full-rank evaluation on the 5th-generation tensor cores (tcgen05 + TMEM), bit-exact by construction.
+//
+// position[u] = #(candidates c : score(u,c) >= score(u, held-out))  (utils.py:253-254), score = the pinned fp32 fma chain.
+//
+//   1. prep   P-tile and Q are split into bf16 hi + lo parts and written as ready-made shared-memory IMAGES: per 128-row
+//             tile, per 64-element K chunk, a 16 KB block already in the SWIZZLE_128B K-major layout tcgen05 expects.
+//             K is the concatenation  A' = [a_hi | a_hi | a_lo],  B' = [b_hi | b_lo | b_hi]  (K' = 3d), so ONE bf16 GEMM
+//             accumulates a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32:  |s_tc - s_fp32chain| <= gamma ||p|| ||q||.
+//   2. GEMM   one CTA = 128 users x a range of item tiles.  Warp 0: producer, one elected lane streams the 16 KB chunk
+//             images with cp.async.bulk (TMA engine, mbarrier complete_tx).  Warp 1: allocates TMEM, one elected lane
+//             issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) into a double-buffered fp32 accumulator
+//             (2 x 128 TMEM columns), tcgen05.commit frees smem stages / publishes accumulators.  Warps 2-5: epilogue,
+//             tcgen05.ld 32 columns at a time, each thread owns one user row:
+//                   s - s_pos >  eps  -> counted            s - s_pos < -eps -> not counted
+//                   otherwise         -> (user, item) appended to the ambiguous list      eps = gamma ||p_u|| ||q_c||
+//             The score matrix never leaves TMEM/registers.
+//   3. exact  the ambiguous pairs are re-scored with the fp32 fma chain (eval.cu order) and counted; train items and the
+//             held-out item are removed by the sparse correction kernel of eval.cu.
+// Every mbarrier wait is bounded (error flag instead of a hang).
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace apr {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_KC = 64;
+constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16)
+constexpr int TC_NORM_BYTES = 512;         // 128 fp32 norms per item tile
+constexpr int TC_NORM_SLOTS = 8;         // smem ring of item-norm blocks (0 slots: the epilogue reads them from global)
+constexpr int TC_THREADS = 192;            // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int TC_AMB_PER_USER = 256;       // capacity of the ambiguous list = n_users * this
+
+struct TcLayout { int nchunk, kpad; int64_t tile_bytes; };
+static inline TcLayout tc_layout(int d) {
+  TcLayout L;
+  L.kpad = (3 * d + TC_KC - 1) / TC_KC * TC_KC;
+  L.nchunk = L.kpad / TC_KC;
+  L.tile_bytes = int64_t(L.nchunk) * TC_CHUNK_BYTES + TC_NORM_BYTES;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: fp32 rows -> swizzled bf16 split images
+// ------------------------------------------------------------------------------------------------
+// one thread per (row, 16-byte piece = 8 consecutive K' elements).  is_a: A' = [hi|hi|lo]; else B' = [hi|lo|hi].
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const float* __restrict__ T, int d, const int32_t* __restrict__ row_ids, int row_lo, int n_rows,
+               int nchunk, int64_t tile_bytes, int is_a, float gamma, unsigned char* __restrict__ img,
+               float* __restrict__ user_scale) {
+  const int pieces = nchunk * 8;
+  const int64_t total = int64_t((n_rows + 127) / 128) * 128 * pieces;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t rr = t / pieces;            // row index inside the padded range
+    const int pc = int(t - rr * pieces);
+    const int tile = int(rr >> 7), r = int(rr & 127);
+    const int chunk = pc >> 3, cpiece = pc & 7;
+    const int k0 = pc * 8;                    // first K' element of this piece
+    __nv_bfloat16 out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = __float2bfloat16_rn(0.f);
+    if (rr < n_rows && k0 < 3 * d) {
+      const int seg = k0 / d, kk = k0 - seg * d;  // d % 8 == 0: a piece never straddles segments
+      const int64_t src_row = row_ids ? int64_t(row_ids[rr]) : int64_t(row_lo) + rr;
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + kk));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + kk + 4));
+      const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const bool want_lo = is_a ? (seg == 2) : (seg == 1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x[e]);
+        out[e] = want_lo ? __float2bfloat16_rn(x[e] - __bfloat162float(hi)) : hi;
+      }
+    }
+    unsigned char* dst = img + int64_t(tile) * tile_bytes + int64_t(chunk) * TC_CHUNK_BYTES + r * 128 + ((cpiece ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(out);
+    if (pc == 0) {
+      // row norm (fp32): items -> appended to the tile image; users -> gamma * ||p|| (slightly inflated)
+      float ss = 0.f;
+      if (rr < n_rows) {
+        const int64_t src_row = row_ids ? int64_t(row_ids[rr]) : int64_t(row_lo) + rr;
+        for (int k = 0; k < d; ++k) { const float v = __ldg(T + src_row * d + k); ss = fmaf(v, v, ss); }
+      }
+      const float nrm = sqrtf(ss) * 1.0001f;
+      if (is_a) { if (rr < n_rows) user_scale[rr] = gamma * nrm * 1.0001f; }
+      else *reinterpret_cast<float*>(img + int64_t(tile) * tile_bytes + int64_t(nchunk) * TC_CHUNK_BYTES + r * 4) = nrm;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: ~2 s at 2 GHz, then *err = 1 and give up (never hang the GPU)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); return false; }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO 1 | SBO 1024>>4 |
+// version 1 (bits 46-47) | layout SWIZZLE_128B = 2 (bits 61-63)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM + counting kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int nchunk,
+                int64_t tile_bytes, int nstage, int norm_slots, int n_users, const float* __restrict__ spos,
+                const float* __restrict__ user_scale, int item_lo, int item_hi, int tiles_total, int tiles_per_cta,
+                int32_t* __restrict__ position, int2* __restrict__ amb, int* __restrict__ amb_count, int amb_cap,
+                int* __restrict__ err) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: align by hand (the launch reserves the slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;                                        // nchunk x 16 KB
+  unsigned char* sB = sA + size_t(nchunk) * TC_CHUNK_BYTES;        // nstage x 16 KB
+  float* sNorm = reinterpret_cast<float*>(sB + size_t(nstage) * TC_CHUNK_BYTES);  // norm_slots x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + norm_slots * 128);
+  // bars: [0,nstage) full, [nstage,2nstage) empty, then tfull[2], tempty[2], afull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * nstage + 5);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (nstage + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * nstage + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * nstage + 2 + b); };
+  const uint32_t afull_bar = bar0 + 8u * (2 * nstage + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(tiles_total, t_begin + tiles_per_cta);
+  const int ntile = max(0, t_end - t_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    mbar_init(afull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: one lane streams the pre-swizzled images through the TMA engine =====
+    if (lane == 0 && ntile > 0) {
+      mbar_expect_tx(afull_bar, uint32_t(nchunk) * TC_CHUNK_BYTES);
+      const unsigned char* asrc = a_img + int64_t(blockIdx.x) * tile_bytes;
+      for (int c = 0; c < nchunk; ++c)
+        bulk_g2s(smem_u32(sA + size_t(c) * TC_CHUNK_BYTES), asrc + size_t(c) * TC_CHUNK_BYTES, TC_CHUNK_BYTES, afull_bar);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int t = 0; t < ntile && ok; ++t) {
+        const unsigned char* bsrc = b_img + int64_t(t_begin + t) * tile_bytes;
+        for (int c = 0; c < nchunk && ok; ++c) {
+          ok = mbar_wait(empty_bar(stage), phase ^ 1u, err);
+          const uint32_t bytes = TC_CHUNK_BYTES + ((c == 0 && norm_slots) ? TC_NORM_BYTES : 0);
+          mbar_expect_tx(full_bar(stage), bytes);
+          bulk_g2s(smem_u32(sB + size_t(stage) * TC_CHUNK_BYTES), bsrc + size_t(c) * TC_CHUNK_BYTES, TC_CHUNK_BYTES, full_bar(stage));
+          if (c == 0 && norm_slots)
+            bulk_g2s(smem_u32(sNorm + (t % norm_slots) * 128), bsrc + size_t(nchunk) * TC_CHUNK_BYTES, TC_NORM_BYTES,
+                     full_bar(stage));
+          if (++stage == nstage) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: a single thread drives the tensor core =====
+    if (lane == 0 && ntile > 0) {
+      bool ok = mbar_wait(afull_bar, 0, err);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntile && ok; ++t) {
+        const int buf = t & 1;
+        ok = mbar_wait(tempty_bar(buf), ((t >> 1) & 1u) ^ 1u, err);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(buf * TC_BN);
+        for (int c = 0; c < nchunk && ok; ++c) {
+          ok = mbar_wait(full_bar(stage), phase, err);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + size_t(c) * TC_CHUNK_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + size_t(stage) * TC_CHUNK_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
+            tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128, (c | k) ? 1u : 0u);
+          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == nstage) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(buf));      // accumulator of this tile complete
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers, one user row per thread =====
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;
+    const int uidx = m0 + m;
+    const bool uvalid = uidx < n_users;
+    const float sp = uvalid ? spos[uidx] : CUDART_INF_F;
+    const float gu = uvalid ? user_scale[uidx] : 0.f;
+    int cnt = 0;
+    bool ok = true;
+    for (int t = 0; t < ntile && ok; ++t) {
+      const int buf = t & 1;
+      ok = mbar_wait(tfull_bar(buf), (t >> 1) & 1u, err);
+      tc_fence_after();
+      const float* qn = norm_slots ? sNorm + (t % norm_slots) * 128
+                                   : reinterpret_cast<const float*>(b_img + int64_t(t_begin + t) * tile_bytes +
+                                                                    int64_t(nchunk) * TC_CHUNK_BYTES);
+      const int n0 = item_lo + (t_begin + t) * TC_BN;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_BN / 32; ++cb) {
+        float v[32];
+        tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_BN + cb * 32), v);
+#pragma unroll
+        for (int jx = 0; jx < 32; ++jx) {
+          const int item = n0 + cb * 32 + jx;
+          const float diff = v[jx] - sp;
+          const float e = gu * qn[cb * 32 + jx];
+          if (item < item_hi && uvalid) {
+            if (diff > e) ++cnt;
+            else if (diff >= -e) {
+              const int slot = atomicAdd(amb_count, 1);
+              if (slot < amb_cap) amb[slot] = make_int2(uidx, item);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+    if (uvalid && cnt) atomicAdd(&position[uidx], cnt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// exact re-scoring of the ambiguous (user, item) pairs
+__global__ void __launch_bounds__(256)
+tc_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
+                  const float* __restrict__ spos, const int2* __restrict__ amb, const int* __restrict__ amb_count,
+                  int amb_cap, int32_t* __restrict__ position) {
+  const int n = min(*amb_count, amb_cap);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int2 a = amb[t];
+    const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
+    const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
+    float acc = 0.f;
+    for (int e = 0; e < d / 4; ++e) {
+      const float4 x = __ldg(p4 + e), y = __ldg(q4 + e);
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
+  }
+}
+
+struct TcWs { int64_t off_spos, off_scale, off_aimg, off_bimg, off_amb, off_cnt, total; int n_utiles, n_itiles; };
+static TcWs tc_ws(int n_users, int n_items, int d) {
+  const TcLayout L = tc_layout(d);
+  TcWs w;
+  w.n_utiles = (n_users + TC_BM - 1) / TC_BM;
+  w.n_itiles = (n_items + TC_BN - 1) / TC_BN;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o += (bytes + 1023) & ~int64_t(1023); return r; };
+  w.off_spos = take(int64_t(n_users) * 4);
+  w.off_scale = take(int64_t(n_users) * 4);
+  w.off_aimg = take(int64_t(w.n_utiles) * L.tile_bytes);
+  w.off_bimg = take(int64_t(w.n_itiles) * L.tile_bytes);
+  w.off_amb = take(int64_t(n_users) * TC_AMB_PER_USER * 8);
+  w.off_cnt = take(16);
+  w.total = o;
+  return w;
+}
+
+// host-side launchers defined in eval.cu
+int launch_score_pairs(const float* P, const float* Q, int d, const int32_t* users, const int32_t* items, int64_t n,
+                       float* scores, cudaStream_t st);
+int launch_excl_correction(const float* P, const float* Q, int d, const int32_t* users, int n_users, const float* spos,
+                           int item_lo, int item_hi, const int64_t* excl_ptr, const int32_t* excl_idx, int32_t* position,
+                           cudaStream_t st);
+
+}  // namespace apr
+
+using namespace apr;
+
+extern "C" {
+
+int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d) {
+  if (n_users < 1 || n_items < 1 || !valid_dim(d) || (d % 8) != 0 || d > 256) return -1;
+  return tc_ws(n_users, n_items, d).total;
+}
+
+int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                         int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                         const int32_t* excl_idx, int32_t* position, void* ws, int64_t ws_bytes, int32_t* err_flag,
+                         apr_stream_t stream) {
+  if (!P || !Q || !users || !test_item || !excl_ptr || !position || !ws || !err_flag) return APR_E_ARG;
+  if (n_users < 1 || item_hi <= item_lo || item_lo < 0 || !valid_dim(d)) return APR_E_ARG;
+  if ((d % 8) != 0 || d > 256) return APR_E_UNSUPPORTED;
+  if (!aligned16(P) || !aligned16(Q) || (reinterpret_cast<uintptr_t>(ws) & 1023u)) return APR_E_ALIGN;
+  const int n_items = item_hi - item_lo;
+  const TcLayout L = tc_layout(d);
+  const TcWs W = tc_ws(n_users, n_items, d);
+  if (ws_bytes < W.total) return APR_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* spos = reinterpret_cast<float*>(base + W.off_spos);
+  float* uscale = reinterpret_cast<float*>(base + W.off_scale);
+  unsigned char* a_img = reinterpret_cast<unsigned char*>(base + W.off_aimg);
+  unsigned char* b_img = reinterpret_cast<unsigned char*>(base + W.off_bimg);
+  int2* amb = reinterpret_cast<int2*>(base + W.off_amb);
+  int* amb_count = reinterpret_cast<int*>(base + W.off_cnt);
+  const int amb_cap = int(std::min<int64_t>(int64_t(n_users) * TC_AMB_PER_USER, 0x7fffffff));
+  // |s_tc - s_chain| <= gamma ||p|| ||q||:  3*2^-16 (dropped lo*lo and split residuals) + (3d + d) 2^-23 (fp32 accumulation
+  // of the tensor core, worst case, plus the rounding of the fma chain itself)
+  const float gamma = 3.0f / 65536.0f + float(4 * d) / 8388608.0f;
+  const int sms = sm_count();
+  auto grid_for = [&](int64_t n) { return int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(sms) * 16))); };
+
+  APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 16, st));
+  { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
+  tc_prep_kernel<<<grid_for(int64_t(W.n_utiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
+      P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, gamma, a_img, uscale);
+  tc_prep_kernel<<<grid_for(int64_t(W.n_itiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
+      Q, d, nullptr, item_lo, n_items, L.nchunk, L.tile_bytes, 0, gamma, b_img, nullptr);
+  APR_LAUNCH_CHECK();
+
+  // shared memory: 1024 alignment slack + A image + B stages + (optional) norm ring + barriers
+  const size_t max_smem = 227 * 1024;
+  const size_t fixed_smem = 1024 + size_t(L.nchunk) * TC_CHUNK_BYTES + 256;
+  int norm_slots = TC_NORM_SLOTS;
+  if (fixed_smem + 2 * size_t(TC_CHUNK_BYTES) + size_t(norm_slots) * TC_NORM_BYTES > max_smem) norm_slots = 0;
+  if (fixed_smem + size_t(TC_CHUNK_BYTES) > max_smem) return APR_E_UNSUPPORTED;
+  int nstage = int((max_smem - fixed_smem - size_t(norm_slots) * TC_NORM_BYTES) / TC_CHUNK_BYTES);
+  nstage = std::max(1, std::min(nstage, 8));
+  const size_t smem = fixed_smem + size_t(norm_slots) * TC_NORM_BYTES + size_t(nstage) * TC_CHUNK_BYTES;
+  APR_CUDA_CHECK(cudaFuncSetAttribute(tc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  // split the item tiles so that the grid has about two waves of CTAs (one CTA per SM: TMEM + smem)
+  const int target = 2 * sms;
+  int splits = std::max(1, std::min((target + W.n_utiles - 1) / W.n_utiles, W.n_itiles));
+  const int per = (W.n_itiles + splits - 1) / splits;
+  splits = (W.n_itiles + per - 1) / per;
+  tc_count_kernel<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, n_users,
+                                                                      spos, uscale, item_lo, item_hi, W.n_itiles, per,
+                                                                      position, amb, amb_count, amb_cap, err_flag);
+  APR_LAUNCH_CHECK();
+  tc_rescore_kernel<<<grid_for(int64_t(n_users) * 32), 256, 0, st>>>(P, Q, d, users, spos, amb, amb_count, amb_cap, position);
+  APR_LAUNCH_CHECK();
+  return launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st);
+}
+
+/* number of ambiguous pairs of the last apr_eval_fullrank_tc call on this workspace (synchronises the stream);
+ * a value above n_users * 256 means the list overflowed and the result is invalid (use the exact path). */
+int apr_eval_tc_ambiguous(const void* ws, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
+                          apr_stream_t stream) {
+  if (!ws || !count_host || n_users < 1 || n_items < 1 || !valid_dim(d)) return APR_E_ARG;
+  const TcWs W = tc_ws(n_users, n_items, d);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  APR_CUDA_CHECK(cudaMemcpyAsync(count_host, static_cast<const char*>(ws) + W.off_cnt, 4, cudaMemcpyDeviceToHost, st));
+  APR_CUDA_CHECK(cudaStreamSynchronize(st));
+  return APR_OK;
+}
+
+}  // extern "C"

@@ -451,6 +451,14 @@ __device__ __forceinline__ void adv_triple(const StepCtx& c, const int4 rc, floa
 
 struct StepStats { float loss, correct; };
 
+template <int G>
+__device__ __forceinline__ int4 shfl4(unsigned mask, const int4 v, int src) {
+  int4 r;
+  r.x = __shfl_sync(mask, v.x, src, G); r.y = __shfl_sync(mask, v.y, src, G);
+  r.z = __shfl_sync(mask, v.z, src, G); r.w = __shfl_sync(mask, v.w, src, G);
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // FAST segment: one triple, both items singletons.  Six row reads, six row writes, everything else in registers.
 // The adversarial forward is evaluated in closed form from four row reductions (S_pq, S_pn, S_pp, S_dd with
@@ -539,15 +547,40 @@ __device__ __forceinline__ void fast_segment(const StepCtx& c, const int user, c
   }
 }
 
-// fast segments k in [k0, k1) of the partitioned header array; one lane group per segment, grid-stride
+// fast segments k in [k0, k1) of the partitioned header array; one lane group per segment, grid-stride.
+// Sharded tables: a segment is processed by the rank that OWNS ITS USER ROW (P and its accumulator stay local; only
+// item rows cross NVLink).  Each lane fetches one header, a ballot finds the rank's own, shuffles broadcast them.
 template <int G, int V, bool FULL>
 __device__ __forceinline__ void fast_range(const StepCtx& c, int s, int k0, int k1, int gid, int ngroups, int lane,
                                            unsigned mask, StepStats& st) {
   const int4* seg_hdr = c.seg_hdr + int64_t(s) * c.B * 2;
-  for (int k = k0 + gid * c.nranks + c.rank; k < k1; k += ngroups * c.nranks) {
-    const int user = __ldg(&seg_hdr[2 * k].x);
-    const int2 ij = __ldg(reinterpret_cast<const int2*>(&seg_hdr[2 * k + 1]));
-    fast_segment<G, V, FULL>(c, user, ij.x, ij.y, lane, mask, st);
+  if (c.nranks == 1) {
+    for (int k = k0 + gid; k < k1; k += ngroups) {
+      const int user = __ldg(&seg_hdr[2 * k].x);
+      const int2 ij = __ldg(reinterpret_cast<const int2*>(&seg_hdr[2 * k + 1]));
+      fast_segment<G, V, FULL>(c, user, ij.x, ij.y, lane, mask, st);
+    }
+    return;
+  }
+  const int gshift = (threadIdx.x & 31) / G * G;  // first lane of this group inside its warp
+  for (int base = k0 + gid * G; base < k1; base += ngroups * G) {
+    const int k = base + lane;
+    int user = -1;
+    int2 ij = make_int2(0, 0);
+    if (k < k1) {
+      user = __ldg(&seg_hdr[2 * k].x);
+      ij = __ldg(reinterpret_cast<const int2*>(&seg_hdr[2 * k + 1]));
+    }
+    const bool mine = k < k1 && (user & (c.nranks - 1)) == c.rank;
+    unsigned m = (__ballot_sync(mask, mine) & mask) >> gshift;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int us = __shfl_sync(mask, user, src, G);
+      const int is = __shfl_sync(mask, ij.x, src, G);
+      const int js = __shfl_sync(mask, ij.y, src, G);
+      fast_segment<G, V, FULL>(c, us, is, js, lane, mask, st);
+    }
   }
 }
 
@@ -703,9 +736,21 @@ __device__ __forceinline__ void general_stage(const StepCtx& c, int s, int stage
   const int ng = c.nslow[s];
   const int4* seg_hdr = c.seg_hdr + int64_t(s) * B * 2;
   const int4* rec = c.rec + int64_t(s) * B;
-  for (int k0 = gid * c.nranks + c.rank; k0 < ng; k0 += ngroups * c.nranks) {
-    const int4 h0 = __ldg(&seg_hdr[2 * k0]);
-    const int4 h1 = __ldg(&seg_hdr[2 * k0 + 1]);
+  const int gshift = (threadIdx.x & 31) / G * G;
+  const int C = min(G, c.nranks);  // headers fetched per iteration: ~one of them belongs to this rank
+  for (int base = gid * C; base < ng; base += ngroups * C) {
+   // one header per lane, ballot the segments whose user row this rank owns, process them one by one
+   int4 hv0 = make_int4(-1, 0, 0, 0), hv1 = make_int4(0, 0, 0, 0);
+   const bool have = lane < C && base + lane < ng;
+   if (have) { hv0 = __ldg(&seg_hdr[2 * (base + lane)]); hv1 = __ldg(&seg_hdr[2 * (base + lane) + 1]); }
+   const bool mine = have && (hv0.x & (c.nranks - 1)) == c.rank;
+   unsigned m = (__ballot_sync(mask, mine) & mask) >> gshift;
+   while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int k0 = base + src;
+    const int4 h0 = shfl4<G>(mask, hv0, src);
+    const int4 h1 = shfl4<G>(mask, hv1, src);
     const bool shared = h0.w != 0;
     if (stage == 0) {
       if (shared) slow_plain<G, V>(c, k0, h0, h1, rec, lane, mask, st);
@@ -714,6 +759,7 @@ __device__ __forceinline__ void general_stage(const StepCtx& c, int s, int stage
     } else {
       segment_complete<G, V>(c, h0, h1, rec, lane, mask, st);
     }
+   }
   }
 }
 
@@ -1147,6 +1193,78 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.flags = 0;
   c.s_begin = step; c.s_end = step + 1; c.only_stage = stage;
   return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream));
+}
+
+// Cross-rank barrier on peer-mapped signal words: rank r stores `epoch` into slot [r] of every peer's signal array and
+// waits until all of its own slots reach `epoch`.  Stream ordered (one tiny kernel); spins are bounded (~2 s) and set
+// *err instead of hanging.  Everything the earlier kernels of this stream wrote (also to peer memory) is complete at the
+// kernel boundary; the system-scope fences order it with the signal.  The pointer array travels as a kernel parameter.
+struct SigArray { int* p[kMaxRanks]; };
+__global__ void xbarrier_launch(SigArray sig, int nranks, int rank, int epoch, int* err) {
+  const int t = threadIdx.x;
+  if (t >= nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(sig.p[t] + rank), "r"(epoch) : "memory");
+  const int* src = sig.p[rank] + t;
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); break; }
+    __nanosleep(64);
+  } while (true);
+  __threadfence_system();
+}
+
+static int g_xbarrier_epoch = 0;
+
+// Steps [first_step, first_step+count) on row-sharded tables, everything launched from here: per step the fast kernel on
+// the second stream, the general stages on the caller's stream with a cross-rank barrier after the plain stage, after
+// the adversarial stage and at the end of the step.  sig = nranks peer pointers to >= nranks ints each (zeroed once);
+// err = device int32 of this rank.  Every rank must make the same sequence of calls.
+int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                            float* const* GQb, float* const* HQb, int32_t* const* sig, int32_t nranks, int32_t rank,
+                            int32_t d, int32_t S, int32_t B, float lr, float reg, float reg_adv, float eps, int32_t adver,
+                            void* ws, int64_t ws_bytes, float* stats, int32_t first_step, int32_t count, int32_t* err,
+                            apr_stream_t stream) {
+  if (!sig || !err || count < 1 || first_step < 0 || first_step + count > S) return APR_E_ARG;
+  AuxStream& ax = aux_stream();
+  if (!ax.ok) return APR_E_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SigArray sa;
+  for (int r = 0; r < kMaxRanks; ++r) sa.p[r] = r < nranks ? sig[r] : nullptr;
+  auto barrier = [&]() -> int {
+    if (nranks == 1) return APR_OK;
+    xbarrier_launch<<<1, 32, 0, st>>>(sa, nranks, rank, ++g_xbarrier_epoch, err);
+    APR_LAUNCH_CHECK();
+    return APR_OK;
+  };
+  for (int s = first_step; s < first_step + count; ++s) {
+    int rc;
+    APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
+    APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
+    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                                 ws_bytes, stats, s, 3, ax.stream);
+    if (rc) return rc;
+    APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+    if (adver) {
+      rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                                   ws_bytes, stats, s, 0, st);
+      if (rc) return rc;
+      if ((rc = barrier())) return rc;
+    }
+    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                                 ws_bytes, stats, s, 1, st);
+    if (rc) return rc;
+    if ((rc = barrier())) return rc;
+    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                                 ws_bytes, stats, s, 2, st);
+    if (rc) return rc;
+    APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
+    if ((rc = barrier())) return rc;
+  }
+  return APR_OK;
 }
 
 int apr_train_unique_counts(const void* ws, int32_t S, int32_t B, int32_t d, int32_t* counts_host, apr_stream_t stream) {

@@ -99,15 +99,15 @@ class ShardedTables(object):
     torch symmetric-memory buffer per rank, so every rank holds the peer (NVLink) address of every shard;
     ``symmetric=False`` builds all G shards in this process's own memory (single-GPU emulation used by the tests)."""
 
-    NAMES = ("P", "accP", "Q", "accQ", "GQ", "HQ")
+    NAMES = ("P", "accP", "Q", "accQ", "GQ", "HQ", "sig")
 
     def __init__(self, rows_p: int, rows_q: int, d: int, batch_global: int, device, world: int = 1, rank: int = 0,
                  group=None, symmetric: bool = False):
         assert world in (1, 2, 4, 8), "row sharding needs a power-of-two number of ranks <= 8"
         self.rows_p, self.rows_q, self.d, self.world, self.rank, self.device = rows_p, rows_q, d, world, rank, device
         lp, lq, ls = -(-rows_p // world), -(-rows_q // world), batch_global // world + 2
-        self.local_rows = {"P": lp, "accP": lp, "Q": lq, "accQ": lq, "GQ": ls, "HQ": ls}
-        sizes = [self.local_rows[n] * d for n in self.NAMES]
+        self.local_rows = {"P": lp, "accP": lp, "Q": lq, "accQ": lq, "GQ": ls, "HQ": ls, "sig": max(1, -(-64 // d))}
+        sizes = [self.local_rows[n] * d for n in self.NAMES]  # "sig": >= 64 words reinterpreted as int32 signal slots
         offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         total = int(offs[-1])
         self.handle = None
@@ -126,6 +126,8 @@ class ShardedTables(object):
         for v in self.views.values():
             v["GQ"].zero_()
             v["HQ"].zero_()
+            v["sig"].zero_()
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
 
     def local(self, name: str, rank: Optional[int] = None) -> torch.Tensor:
         return self.views[self.rank if rank is None else rank][name]
@@ -182,6 +184,11 @@ def train_steps_sharded(tables: ShardedTables, U: torch.Tensor, I: torch.Tensor,
             for off, step_bytes, _ in views.values():
                 dist.broadcast(wsb[off + s0 * step_bytes: off + (s0 + ns) * step_bytes], src=dist.get_global_rank(group, src)
                                if group is not None else src, group=group)
+        if len(ranks) == 1:
+            # real run: the library issues every launch and cross-rank barrier of these steps itself
+            engine.train_steps_sharded(tables.ptrs, G, ranks[0], d, S, Bg, lr, reg, reg_adv, eps, adver, ws, s0, ns,
+                                       tables.err, stats)
+            continue
         for s in range(s0, s0 + ns):
             launch = lambda r, stage: engine.train_stage_sharded(tables.ptrs, G, r, d, S, Bg, lr, reg, reg_adv, eps, adver,
                                                                  ws, s, stage, stats)

@@ -172,6 +172,20 @@ def train_stage_sharded(ptrs: dict, nranks: int, rank: int, d: int, n_steps: int
                                                   _ptr(stats, torch.float32), step, stage, _stream()))
 
 
+def train_steps_sharded(ptrs: dict, nranks: int, rank: int, d: int, n_steps: int, batch: int, lr, reg, reg_adv, eps, adver,
+                        ws: "TrainWorkspace", first_step: int, count: int, err: torch.Tensor,
+                        stats: Optional[torch.Tensor] = None) -> None:
+    """Steps [first_step, first_step+count) of the sharded path, all launches and cross-rank barriers issued by the
+    library.  ``ptrs`` additionally maps "sig" to the ranks' signal-word pointers."""
+    a = ptrs.get("_c7")
+    if a is None:
+        a = ptrs["_c7"] = [_ptr_array(ptrs[k]) for k in ("P", "Q", "accP", "accQ", "GQ", "HQ", "sig")]
+    _lib.check(_lib.lib().apr_train_steps_sharded(*a, nranks, rank, d, n_steps, batch, float(lr), float(reg), float(reg_adv),
+                                                  float(eps), int(bool(adver)), ws.buf.data_ptr(), ws.nbytes,
+                                                  _ptr(stats, torch.float32), first_step, count, _ptr(err, torch.int32),
+                                                  _stream()))
+
+
 def loss_acc(P, Q, u, i, j) -> torch.Tensor:
     """-> float64 [S,2]: per batch {sum softplus(-r), count(x>0)} (utils.py:159-175)."""
     S, B = u.shape
@@ -221,6 +235,44 @@ def eval_fullrank(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, 
                                             _ptr(excl_idx, torch.int32), k_top, _ptr(position, torch.int32), _ptr(ids),
                                             _ptr(sc), int(bool(exact)), ws.data_ptr(), ws.numel(), _stream()))
     return position, ids, sc
+
+
+def tc_supported(d: int) -> bool:
+    return d % 8 == 0 and d <= 256
+
+
+def eval_fullrank_tc(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, excl_idx,
+                     position: Optional[torch.Tensor] = None, check: bool = True):
+    """Positions through the tcgen05 bf16x3 filter + exact re-scoring (same results as eval_fullrank(exact=True)).
+    -> (position, n_ambiguous).  ``check`` synchronises to verify the pipeline flag and the ambiguous-list capacity."""
+    n = users.numel()
+    d = P.shape[1]
+    dev = P.device
+    if position is None:
+        position = torch.zeros(n, dtype=torch.int32, device=dev)
+    n_items = item_hi - item_lo
+    nbytes = _lib.lib().apr_eval_tc_workspace_bytes(n, n_items, d)
+    if nbytes < 0:
+        raise ValueError("tensor-core evaluation needs d % 8 == 0 and d <= 256")
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    if excl_idx.numel() == 0:
+        excl_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().apr_eval_fullrank_tc(_ptr(P, torch.float32), _ptr(Q, torch.float32), d, _ptr(users, torch.int32),
+                                               _ptr(test_item, torch.int32), n, item_lo, item_hi, _ptr(excl_ptr, torch.int64),
+                                               _ptr(excl_idx, torch.int32), _ptr(position, torch.int32), ws.data_ptr() + off,
+                                               nbytes, _ptr(err), _stream()))
+    n_amb = -1
+    if check:
+        c = ctypes.c_int32(0)
+        _lib.check(_lib.lib().apr_eval_tc_ambiguous(ws.data_ptr() + off, n, n_items, d, ctypes.byref(c), _stream()))
+        n_amb = c.value
+        if int(err.item()) != 0:
+            raise RuntimeError("tcgen05 evaluation pipeline timed out (error flag set)")
+        if n_amb > n * 256:
+            raise RuntimeError("ambiguous list overflow (%d pairs): use the exact path" % n_amb)
+    return position, n_amb
 
 
 def sum_squares(x: torch.Tensor) -> torch.Tensor:

@@ -116,6 +116,17 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
                             void* workspace, int64_t workspace_bytes, float* stats, int32_t step, int32_t stage,
                             apr_stream_t stream);
 
+/* The whole per-step sequence of the sharded path launched from the library (no host work between steps): fast kernel
+ * on the internal second stream, general stages on `stream`, and a cross-rank barrier (peer-mapped signal words,
+ * bounded spin) after the plain stage, after the adversarial stage and at the end of every step.  sig_host = HOST array
+ * of nranks device pointers to >= nranks int32 each (every rank's signal words, zeroed once); err = this rank's device
+ * int32, set non-zero if a barrier timed out.  Every rank must issue the same sequence of calls. */
+int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                            float* const* GQb, float* const* HQb, int32_t* const* sig_host, int32_t nranks, int32_t rank,
+                            int32_t d, int32_t n_steps, int32_t batch, float lr, float reg, float reg_adv, float eps,
+                            int32_t adver, void* workspace, int64_t workspace_bytes, float* stats, int32_t first_step,
+                            int32_t count, int32_t* err, apr_stream_t stream);
+
 /* ---- A9 / K7: training_loss_acc, utils.py:159-175 (output_adv = 0): per batch s,
  *      out[2s] = sum_b softplus(-clip(x_b)), out[2s+1] = count(x_b > 0), as float64. */
 int apr_loss_acc(const float* P, const float* Q, int32_t d, const int32_t* u, const int32_t* i, const int32_t* j,
@@ -146,6 +157,20 @@ int apr_eval_fullrank(const float* P, const float* Q, int32_t d, const int32_t* 
                       int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
                       const int32_t* excl_idx, int32_t k_top, int32_t* position, int32_t* topk_ids, float* topk_scores,
                       int32_t exact, void* workspace, int64_t workspace_bytes, apr_stream_t stream);
+
+/* ---- A10 / K9 on the tensor cores: the same positions as apr_eval_fullrank (k_top = 0), computed by a tcgen05 bf16x3
+ *      GEMM with an error-bounded count and exact fp32 re-scoring of the ambiguous candidates (csrc/eval_tc.cu).
+ *      d % 8 == 0, d <= 256.  workspace: apr_eval_tc_workspace_bytes(n_users, item_hi - item_lo, d) bytes, 1024-byte
+ *      aligned.  *err_flag (device int32) is set if a pipeline wait timed out.  apr_eval_tc_ambiguous reports how many
+ *      (user, item) pairs were re-scored; more than n_users * 256 means the list overflowed (result invalid: use the
+ *      exact path). */
+int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d);
+int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                         int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                         const int32_t* excl_idx, int32_t* position, void* workspace, int64_t workspace_bytes,
+                         int32_t* err_flag, apr_stream_t stream);
+int apr_eval_tc_ambiguous(const void* workspace, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
+                          apr_stream_t stream);
 
 /* ---- K11: np.linalg.norm(embedding_P) of utils.py:92-97: *out (device double) = sum of squares. */
 int apr_sum_squares(const float* x, int64_t n, double* out, apr_stream_t stream);

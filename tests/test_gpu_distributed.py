@@ -46,6 +46,7 @@ def _train_worker(rank, world, port, out):
     td = lambda a: torch.from_numpy(a).to(dev)
     train_steps_sharded(t, td(u), td(i), td(j), 0.05, 0.01, 1.0, 0.5, 1, ws, aux_stream=aux)
     torch.cuda.synchronize()
+    assert int(t.err.item()) == 0, "cross-rank barrier timed out"
     dist.barrier()
     # every rank returns its shards; rank 0 reassembles and compares
     parts = {n: t.local(n).cpu() for n in ("P", "Q", "accP", "accQ")}
