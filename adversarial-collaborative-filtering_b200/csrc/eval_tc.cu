@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -30,8 +31,11 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_KC = 64;
 constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16)
 constexpr int TC_NORM_BYTES = 512;         // 128 fp32 norms per item tile
 constexpr int TC_NORM_SLOTS = 8;         // smem ring of item-norm blocks (0 slots: the epilogue reads them from global)
-constexpr int TC_THREADS = 192;            // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
-constexpr int TC_AMB_PER_USER = 256;       // capacity of the ambiguous list = n_users * this
+constexpr int TC_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+// capacity of the ambiguous list: max(256, n_items / 256) pairs per user (~0.4 % of all pairs; ~0.07-0.2 % are expected)
+static inline int64_t tc_amb_cap(int n_users, int n_items) {
+  return std::min<int64_t>(int64_t(n_users) * std::max(256, n_items / 256), 0x7fffff00);
+}
 
 struct TcLayout { int nchunk, kpad; int64_t tile_bytes; };
 static inline TcLayout tc_layout(int d) {
@@ -175,14 +179,15 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   unsigned char* sB = sA + size_t(nchunk) * TC_CHUNK_BYTES;        // nstage x 16 KB
   float* sNorm = reinterpret_cast<float*>(sB + size_t(nstage) * TC_CHUNK_BYTES);  // norm_slots x 128 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + norm_slots * 128);
-  // bars: [0,nstage) full, [nstage,2nstage) empty, then tfull[2], tempty[2], afull
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * nstage + 5);
+  // bars: [0,nstage) full, [nstage,2nstage) empty, then tfull[2], tempty[2], afull, nfull[norm_slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * nstage + 5 + norm_slots);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (nstage + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * nstage + b); };
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * nstage + 2 + b); };
   const uint32_t afull_bar = bar0 + 8u * (2 * nstage + 4);
+  auto nfull_bar = [&](int k) { return bar0 + 8u * (2 * nstage + 5 + k); };  // norm block k of the ring has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
@@ -192,8 +197,9 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_THREADS - 64); }
     mbar_init(afull_bar, 1);
+    for (int k = 0; k < norm_slots; ++k) mbar_init(nfull_bar(k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -219,12 +225,15 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         const unsigned char* bsrc = b_img + int64_t(t_begin + t) * tile_bytes;
         for (int c = 0; c < nchunk && ok; ++c) {
           ok = mbar_wait(empty_bar(stage), phase ^ 1u, err);
-          const uint32_t bytes = TC_CHUNK_BYTES + ((c == 0 && norm_slots) ? TC_NORM_BYTES : 0);
-          mbar_expect_tx(full_bar(stage), bytes);
+          mbar_expect_tx(full_bar(stage), TC_CHUNK_BYTES);
           bulk_g2s(smem_u32(sB + size_t(stage) * TC_CHUNK_BYTES), bsrc + size_t(c) * TC_CHUNK_BYTES, TC_CHUNK_BYTES, full_bar(stage));
-          if (c == 0 && norm_slots)
+          if (c == 0 && norm_slots) {
+            // the item norms ride on their OWN barrier: the epilogue threads acquire it themselves before reading.
+            // (slot reuse is safe: the producer is never more than nstage/nchunk + 2 < norm_slots tiles ahead)
+            mbar_expect_tx(nfull_bar(t % norm_slots), TC_NORM_BYTES);
             bulk_g2s(smem_u32(sNorm + (t % norm_slots) * 128), bsrc + size_t(nchunk) * TC_CHUNK_BYTES, TC_NORM_BYTES,
-                     full_bar(stage));
+                     nfull_bar(t % norm_slots));
+          }
           if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
       }
@@ -255,39 +264,59 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers, one user row per thread =====
+    // ===== epilogue: TMEM -> registers.  Thread = one user row x one half (64) of the tile's columns. =====
+    // Branch-free per element: two threshold compares folded into bit masks; the count is a popcount, the (rare)
+    // ambiguous bits take a slow path after each 32-column block.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which 64 columns of the tile
     const int m = quarter * 32 + lane;
     const int uidx = m0 + m;
     const bool uvalid = uidx < n_users;
     const float sp = uvalid ? spos[uidx] : CUDART_INF_F;
     const float gu = uvalid ? user_scale[uidx] : 0.f;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    int* my_count = amb_count + cta;                       // amb_cap = capacity of ONE CTA's segment
+    int2* my_amb = amb + int64_t(cta) * amb_cap;
     int cnt = 0;
     bool ok = true;
     for (int t = 0; t < ntile && ok; ++t) {
       const int buf = t & 1;
       ok = mbar_wait(tfull_bar(buf), (t >> 1) & 1u, err);
       tc_fence_after();
+      if (norm_slots && ok) ok = mbar_wait(nfull_bar(t % norm_slots), uint32_t(t / norm_slots) & 1u, err);
       const float* qn = norm_slots ? sNorm + (t % norm_slots) * 128
                                    : reinterpret_cast<const float*>(b_img + int64_t(t_begin + t) * tile_bytes +
                                                                     int64_t(nchunk) * TC_CHUNK_BYTES);
       const int n0 = item_lo + (t_begin + t) * TC_BN;
 #pragma unroll 1
-      for (int cb = 0; cb < TC_BN / 32; ++cb) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;
         float v[32];
-        tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_BN + cb * 32), v);
+        tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_BN + col0), v);
+        unsigned hi_mask = 0u, in_mask = 0u;   // bit j: v > sp + e   /   v >= sp - e
 #pragma unroll
-        for (int jx = 0; jx < 32; ++jx) {
-          const int item = n0 + cb * 32 + jx;
-          const float diff = v[jx] - sp;
-          const float e = gu * qn[cb * 32 + jx];
-          if (item < item_hi && uvalid) {
-            if (diff > e) ++cnt;
-            else if (diff >= -e) {
-              const int slot = atomicAdd(amb_count, 1);
-              if (slot < amb_cap) amb[slot] = make_int2(uidx, item);
-            }
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qn + col0 + 4 * j4);
+          const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int jx = 4 * j4 + k;
+            const float e = gu * qv[k];
+            hi_mask |= (v[jx] > sp + e) ? (1u << jx) : 0u;
+            in_mask |= (v[jx] >= sp - e) ? (1u << jx) : 0u;
           }
+        }
+        // columns past item_hi (padding of the last tile) never count
+        const int ncols = min(32, max(0, item_hi - (n0 + col0)));
+        const unsigned colmask = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
+        hi_mask &= colmask;
+        cnt += __popc(hi_mask);
+        unsigned amb_bits = uvalid ? (in_mask & ~hi_mask & colmask) : 0u;
+        while (amb_bits) {
+          const int jx = __ffs(amb_bits) - 1;
+          amb_bits &= amb_bits - 1;
+          const int slot = atomicAdd(my_count, 1);  // per-CTA counter: no chip-wide same-address serialisation
+          if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
         }
       }
       tc_fence_before();
@@ -303,22 +332,25 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   }
 }
 
-// exact re-scoring of the ambiguous (user, item) pairs
+// exact re-scoring of the ambiguous (user, item) pairs; blockIdx.y = the producing CTA's list segment
 __global__ void __launch_bounds__(256)
 tc_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
                   const float* __restrict__ spos, const int2* __restrict__ amb, const int* __restrict__ amb_count,
                   int amb_cap, int32_t* __restrict__ position) {
-  const int n = min(*amb_count, amb_cap);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const int2 a = amb[t];
-    const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
-    const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
-    float acc = 0.f;
-    for (int e = 0; e < d / 4; ++e) {
-      const float4 x = __ldg(p4 + e), y = __ldg(q4 + e);
-      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+  for (int seg = blockIdx.y; seg < int(gridDim.y); seg += gridDim.y) {
+    const int n = min(amb_count[seg], amb_cap);
+    const int2* list = amb + int64_t(seg) * amb_cap;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+      const int2 a = list[t];
+      const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
+      const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
+      float acc = 0.f;
+      for (int e = 0; e < d / 4; ++e) {
+        const float4 x = __ldg(p4 + e), y = __ldg(q4 + e);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+      }
+      if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
     }
-    if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
   }
 }
 
@@ -334,8 +366,8 @@ static TcWs tc_ws(int n_users, int n_items, int d) {
   w.off_scale = take(int64_t(n_users) * 4);
   w.off_aimg = take(int64_t(w.n_utiles) * L.tile_bytes);
   w.off_bimg = take(int64_t(w.n_itiles) * L.tile_bytes);
-  w.off_amb = take(int64_t(n_users) * TC_AMB_PER_USER * 8);
-  w.off_cnt = take(16);
+  w.off_amb = take(tc_amb_cap(n_users, n_items) * 8);
+  w.off_cnt = take(4 * 65536 + 16);  // per-CTA counters
   w.total = o;
   return w;
 }
@@ -378,14 +410,14 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   unsigned char* b_img = reinterpret_cast<unsigned char*>(base + W.off_bimg);
   int2* amb = reinterpret_cast<int2*>(base + W.off_amb);
   int* amb_count = reinterpret_cast<int*>(base + W.off_cnt);
-  const int amb_cap = int(std::min<int64_t>(int64_t(n_users) * TC_AMB_PER_USER, 0x7fffffff));
+  const int amb_cap = int(tc_amb_cap(n_users, n_items));
   // |s_tc - s_chain| <= gamma ||p|| ||q||:  3*2^-16 (dropped lo*lo and split residuals) + (3d + d) 2^-23 (fp32 accumulation
   // of the tensor core, worst case, plus the rounding of the fma chain itself)
   const float gamma = 3.0f / 65536.0f + float(4 * d) / 8388608.0f;
   const int sms = sm_count();
   auto grid_for = [&](int64_t n) { return int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(sms) * 16))); };
 
-  APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 16, st));
+  APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 4 * 65536 + 16, st));
   { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
   tc_prep_kernel<<<grid_for(int64_t(W.n_utiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
       P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, gamma, a_img, uscale);
@@ -395,7 +427,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
 
   // shared memory: 1024 alignment slack + A image + B stages + (optional) norm ring + barriers
   const size_t max_smem = 227 * 1024;
-  const size_t fixed_smem = 1024 + size_t(L.nchunk) * TC_CHUNK_BYTES + 256;
+  const size_t fixed_smem = 1024 + size_t(L.nchunk) * TC_CHUNK_BYTES + 384;
   int norm_slots = TC_NORM_SLOTS;
   if (fixed_smem + 2 * size_t(TC_CHUNK_BYTES) + size_t(norm_slots) * TC_NORM_BYTES > max_smem) norm_slots = 0;
   if (fixed_smem + size_t(TC_CHUNK_BYTES) > max_smem) return APR_E_UNSUPPORTED;
@@ -408,24 +440,38 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   int splits = std::max(1, std::min((target + W.n_utiles - 1) / W.n_utiles, W.n_itiles));
   const int per = (W.n_itiles + splits - 1) / splits;
   splits = (W.n_itiles + per - 1) / per;
+  const int n_ctas = W.n_utiles * splits;
+  if (n_ctas > 65536) return APR_E_UNSUPPORTED;
+  const int cap_cta = int(int64_t(amb_cap) / n_ctas);  // every CTA owns one segment of the list
+  if (cap_cta < 16) return APR_E_UNSUPPORTED;
+  const int32_t meta[2] = {n_ctas, cap_cta};
+  APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
   tc_count_kernel<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, n_users,
                                                                       spos, uscale, item_lo, item_hi, W.n_itiles, per,
-                                                                      position, amb, amb_count, amb_cap, err_flag);
+                                                                      position, amb, amb_count, cap_cta, err_flag);
   APR_LAUNCH_CHECK();
-  tc_rescore_kernel<<<grid_for(int64_t(n_users) * 32), 256, 0, st>>>(P, Q, d, users, spos, amb, amb_count, amb_cap, position);
+  tc_rescore_kernel<<<dim3(std::max(1, std::min(64, cap_cta / 256 + 1)), n_ctas), 256, 0, st>>>(P, Q, d, users, spos, amb,
+                                                                                              amb_count, cap_cta, position);
   APR_LAUNCH_CHECK();
   return launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st);
 }
 
-/* number of ambiguous pairs of the last apr_eval_fullrank_tc call on this workspace (synchronises the stream);
- * a value above n_users * 256 means the list overflowed and the result is invalid (use the exact path). */
+/* number of ambiguous pairs of the last apr_eval_fullrank_tc call on this workspace and the capacity of the list
+ * (synchronises the stream); count > capacity means the list overflowed and the result is invalid (exact path). */
 int apr_eval_tc_ambiguous(const void* ws, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
                           apr_stream_t stream) {
   if (!ws || !count_host || n_users < 1 || n_items < 1 || !valid_dim(d)) return APR_E_ARG;
   const TcWs W = tc_ws(n_users, n_items, d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  APR_CUDA_CHECK(cudaMemcpyAsync(count_host, static_cast<const char*>(ws) + W.off_cnt, 4, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> h(65536 + 2);
+  APR_CUDA_CHECK(cudaMemcpyAsync(h.data(), static_cast<const char*>(ws) + W.off_cnt, (65536 + 2) * 4, cudaMemcpyDeviceToHost, st));
   APR_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int n_ctas = h[65536], cap_cta = h[65537];
+  int64_t total = 0;
+  bool overflow = false;
+  for (int k = 0; k < n_ctas && k < 65536; ++k) { total += h[k]; overflow |= h[k] > cap_cta; }
+  count_host[0] = int32_t(std::min<int64_t>(total, 0x7fffffff));
+  count_host[1] = overflow ? 0 : int32_t(std::min<int64_t>(int64_t(cap_cta) * n_ctas, 0x7fffffff));  // 0 => overflow
   return APR_OK;
 }
 

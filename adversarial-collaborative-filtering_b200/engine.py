@@ -265,13 +265,13 @@ def eval_fullrank_tc(P, Q, users, test_item, item_lo: int, item_hi: int, excl_pt
                                                nbytes, _ptr(err), _stream()))
     n_amb = -1
     if check:
-        c = ctypes.c_int32(0)
-        _lib.check(_lib.lib().apr_eval_tc_ambiguous(ws.data_ptr() + off, n, n_items, d, ctypes.byref(c), _stream()))
-        n_amb = c.value
+        c = (ctypes.c_int32 * 2)()
+        _lib.check(_lib.lib().apr_eval_tc_ambiguous(ws.data_ptr() + off, n, n_items, d, c, _stream()))
+        n_amb = int(c[0])
         if int(err.item()) != 0:
             raise RuntimeError("tcgen05 evaluation pipeline timed out (error flag set)")
-        if n_amb > n * 256:
-            raise RuntimeError("ambiguous list overflow (%d pairs): use the exact path" % n_amb)
+        if n_amb > int(c[1]):
+            raise RuntimeError("ambiguous list overflow (%d pairs > %d): use the exact path" % (n_amb, int(c[1])))
     return position, n_amb
 
 

@@ -161,9 +161,9 @@ int apr_eval_fullrank(const float* P, const float* Q, int32_t d, const int32_t* 
 /* ---- A10 / K9 on the tensor cores: the same positions as apr_eval_fullrank (k_top = 0), computed by a tcgen05 bf16x3
  *      GEMM with an error-bounded count and exact fp32 re-scoring of the ambiguous candidates (csrc/eval_tc.cu).
  *      d % 8 == 0, d <= 256.  workspace: apr_eval_tc_workspace_bytes(n_users, item_hi - item_lo, d) bytes, 1024-byte
- *      aligned.  *err_flag (device int32) is set if a pipeline wait timed out.  apr_eval_tc_ambiguous reports how many
- *      (user, item) pairs were re-scored; more than n_users * 256 means the list overflowed (result invalid: use the
- *      exact path). */
+ *      aligned.  *err_flag (device int32) is set if a pipeline wait timed out.  apr_eval_tc_ambiguous writes
+ *      count_host[0] = (user, item) pairs sent to exact re-scoring, count_host[1] = capacity of that list
+ *      (n_users * max(256, n_items/256)); count > capacity means overflow (result invalid: use the exact path). */
 int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d);
 int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
                          int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
