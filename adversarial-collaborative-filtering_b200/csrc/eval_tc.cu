@@ -37,10 +37,15 @@ static inline int64_t tc_amb_cap(int n_users, int n_items) {
   return std::min<int64_t>(int64_t(n_users) * std::max(256, n_items / 256), 0x7fffff00);
 }
 
-struct TcLayout { int nchunk, kpad; int64_t tile_bytes; };
+// split2 (d % 64 == 0): both operands are stored as [hi | lo] (K' = 2d) and the b_hi stage is multiplied with a_hi AND
+// a_lo, the b_lo stage with a_hi -- the same three products with a third less operand traffic and shared memory.
+// Otherwise K' = 3d: A' = [hi | hi | lo], B' = [hi | lo | hi], zero padded to a multiple of 64.
+struct TcLayout { int nchunk, kpad, split2, cps; int64_t tile_bytes; };
 static inline TcLayout tc_layout(int d) {
   TcLayout L;
-  L.kpad = (3 * d + TC_KC - 1) / TC_KC * TC_KC;
+  L.split2 = (d % TC_KC) == 0;
+  L.cps = d / TC_KC;  // chunks per segment (split2)
+  L.kpad = L.split2 ? 2 * d : (3 * d + TC_KC - 1) / TC_KC * TC_KC;
   L.nchunk = L.kpad / TC_KC;
   L.tile_bytes = int64_t(L.nchunk) * TC_CHUNK_BYTES + TC_NORM_BYTES;
   return L;
@@ -52,7 +57,7 @@ static inline TcLayout tc_layout(int d) {
 // one thread per (row, 16-byte piece = 8 consecutive K' elements).  is_a: A' = [hi|hi|lo]; else B' = [hi|lo|hi].
 __global__ void __launch_bounds__(256)
 tc_prep_kernel(const float* __restrict__ T, int d, const int32_t* __restrict__ row_ids, int row_lo, int n_rows,
-               int nchunk, int64_t tile_bytes, int is_a, float gamma, unsigned char* __restrict__ img,
+               int nchunk, int64_t tile_bytes, int is_a, int split2, float gamma, unsigned char* __restrict__ img,
                float* __restrict__ user_scale) {
   const int pieces = nchunk * 8;
   const int64_t total = int64_t((n_rows + 127) / 128) * 128 * pieces;
@@ -65,13 +70,13 @@ tc_prep_kernel(const float* __restrict__ T, int d, const int32_t* __restrict__ r
     __nv_bfloat16 out[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) out[e] = __float2bfloat16_rn(0.f);
-    if (rr < n_rows && k0 < 3 * d) {
+    if (rr < n_rows && k0 < (split2 ? 2 : 3) * d) {
       const int seg = k0 / d, kk = k0 - seg * d;  // d % 8 == 0: a piece never straddles segments
       const int64_t src_row = row_ids ? int64_t(row_ids[rr]) : int64_t(row_lo) + rr;
       const float4 x0 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + kk));
       const float4 x1 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + kk + 4));
       const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-      const bool want_lo = is_a ? (seg == 2) : (seg == 1);
+      const bool want_lo = split2 ? (seg == 1) : (is_a ? (seg == 2) : (seg == 1));
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const __nv_bfloat16 hi = __float2bfloat16_rn(x[e]);
@@ -168,7 +173,7 @@ constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((T
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int nchunk,
-                int64_t tile_bytes, int nstage, int norm_slots, int n_users, const float* __restrict__ spos,
+                int64_t tile_bytes, int nstage, int norm_slots, int cps, int n_users, const float* __restrict__ spos,
                 const float* __restrict__ user_scale, int item_lo, int item_hi, int tiles_total, int tiles_per_cta,
                 int32_t* __restrict__ position, int2* __restrict__ amb, int* __restrict__ amb_count, int amb_cap,
                 int* __restrict__ err) {
@@ -252,11 +257,20 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         for (int c = 0; c < nchunk && ok; ++c) {
           ok = mbar_wait(full_bar(stage), phase, err);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + size_t(c) * TC_CHUNK_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + size_t(stage) * TC_CHUNK_BYTES));
+          // A chunk(s) this B chunk meets: K'=3d layout -> chunk c; split2 -> b_hi[cc] x {a_hi[cc], a_lo[cc]}, b_lo[cc] x a_hi[cc]
+          const int a0 = cps ? (c % cps) : c;
+          const int a1 = (cps && c < cps) ? cps + c : -1;
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + size_t(a0) * TC_CHUNK_BYTES));
 #pragma unroll
           for (int k = 0; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
             tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128, (c | k) ? 1u : 0u);
+          if (a1 >= 0) {
+            const uint64_t adesc1 = umma_desc_sw128(smem_u32(sA + size_t(a1) * TC_CHUNK_BYTES));
+#pragma unroll
+            for (int k = 0; k < TC_KC / 16; ++k)
+              tc_mma_bf16(tmem_d, adesc1 + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128, 1u);
+          }
           tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
@@ -420,9 +434,9 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 4 * 65536 + 16, st));
   { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
   tc_prep_kernel<<<grid_for(int64_t(W.n_utiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
-      P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, gamma, a_img, uscale);
+      P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, L.split2, gamma, a_img, uscale);
   tc_prep_kernel<<<grid_for(int64_t(W.n_itiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
-      Q, d, nullptr, item_lo, n_items, L.nchunk, L.tile_bytes, 0, gamma, b_img, nullptr);
+      Q, d, nullptr, item_lo, n_items, L.nchunk, L.tile_bytes, 0, L.split2, gamma, b_img, nullptr);
   APR_LAUNCH_CHECK();
 
   // shared memory: 1024 alignment slack + A image + B stages + (optional) norm ring + barriers
@@ -435,9 +449,20 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   nstage = std::max(1, std::min(nstage, 8));
   const size_t smem = fixed_smem + size_t(norm_slots) * TC_NORM_BYTES + size_t(nstage) * TC_CHUNK_BYTES;
   APR_CUDA_CHECK(cudaFuncSetAttribute(tc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  // split the item tiles so that the grid has about two waves of CTAs (one CTA per SM: TMEM + smem)
-  const int target = 2 * sms;
-  int splits = std::max(1, std::min((target + W.n_utiles - 1) / W.n_utiles, W.n_itiles));
+  // one CTA per SM (TMEM + shared memory): split the item tiles so that the CTAs fill whole waves of SMs, with as few
+  // splits as reach >= 92 % wave efficiency and >= 8 item tiles per CTA (amortises the A image and the pipeline fill)
+  int splits = 1;
+  {
+    double best = -1.0;
+    const int max_splits = std::max(1, std::min(W.n_itiles / 8, 512));
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int64_t ctas = int64_t(W.n_utiles) * sp;
+      const int64_t waves = (ctas + sms - 1) / sms;
+      const double eff = double(ctas) / double(waves * sms);
+      if (eff > best + 1e-9) { best = eff; splits = sp; }
+      if (eff >= 0.92) { splits = sp; break; }
+    }
+  }
   const int per = (W.n_itiles + splits - 1) / splits;
   splits = (W.n_itiles + per - 1) / per;
   const int n_ctas = W.n_utiles * splits;
@@ -446,7 +471,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   if (cap_cta < 16) return APR_E_UNSUPPORTED;
   const int32_t meta[2] = {n_ctas, cap_cta};
   APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
-  tc_count_kernel<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, n_users,
+  tc_count_kernel<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, L.split2 ? L.cps : 0, n_users,
                                                                       spos, uscale, item_lo, item_hi, W.n_itiles, per,
                                                                       position, amb, amb_count, cap_cta, err_flag);
   APR_LAUNCH_CHECK();

@@ -274,8 +274,17 @@ def eval_positions(model, feed: EvalInputs, exact: bool = False) -> torch.Tensor
     """Device int32 rank position (#negatives scoring >= the held-out item) of every evaluation user."""
     d = feed.to_device(model.device)
     if feed.mode == "all":
+        if not exact and engine.tc_supported(model.embedding_P.shape[1]) and feed.num_items >= 1024:
+            # tcgen05 bf16x3 filter + exact re-scoring: same positions as the fp32 kernel (tests/test_gpu_eval_tc.py)
+            try:
+                pos, _ = engine.eval_fullrank_tc(model.embedding_P, model.embedding_Q, d["users"], d["test"], 0,
+                                                 feed.num_items, d["excl_ptr"], d["excl_idx"])
+                return pos
+            except RuntimeError as e:  # ambiguous-list overflow (degenerate score distribution): exact kernel
+                if "overflow" not in str(e):
+                    raise
         pos, _, _ = engine.eval_fullrank(model.embedding_P, model.embedding_Q, d["users"], d["test"], 0, feed.num_items,
-                                         d["excl_ptr"], d["excl_idx"], 0, exact=exact)
+                                         d["excl_ptr"], d["excl_idx"], 0, exact=True)
         return pos
     pos, _ = engine.eval_candidates(model.embedding_P, model.embedding_Q, d["users"], d["cand_ptr"], d["cand_idx"])
     return pos

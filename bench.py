@@ -452,40 +452,59 @@ def main_single(args):
 
 
 def bench_eval(torch, engine, dev, tc_peak):
-    """Full-rank leave-one-out evaluation on the yelp-sort shape (25 677 users x 25 815 items, d=128)."""
-    from apr_b200.Dataset import build_sorted_csr
-    U, I, d = 25677, 25815, 128
-    g = torch.Generator(device=dev)
-    g.manual_seed(2019)
-    P = torch.randn((U, d), device=dev, generator=g) / d ** 0.5
-    Q = torch.randn((I + 1, d), device=dev, generator=g) / d ** 0.5
-    rng = np.random.default_rng(7)
-    test = rng.integers(0, I, U).astype(np.int32)
-    lens = rng.integers(5, 60, U)
-    ptr = np.zeros(U + 1, np.int64)
-    ptr[1:] = np.cumsum(lens)
-    idx = np.sort(rng.integers(0, I, int(ptr[-1])).astype(np.int32))
-    # rows must be sorted and unique: build per row from a sorted global draw
-    rows = [np.unique(np.append(rng.integers(0, I, lens[k]), test[k])).astype(np.int32) for k in range(U)]
-    ptr[1:] = np.cumsum([r.size for r in rows])
-    idx = np.concatenate(rows)
-    t = lambda a, dt: torch.from_numpy(a).to(device=dev, dtype=dt)
-    a = [P, Q, t(np.arange(U, dtype=np.int32), torch.int32), t(test, torch.int32), 0, I, t(ptr, torch.int64), t(idx, torch.int32)]
+    """Full-rank leave-one-out evaluation (second headline metric): users/s with positions for HR@10/NDCG@10.
+    Shapes: BASELINE.json configs[2] (yelp-sort shape, d=128) and a tile of configs[4] (10M items, d=256)."""
     out = {}
-    for name, k_top in (("position_only", 0), ("with_top10", 10)):
-        engine.eval_fullrank(*a, k_top)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        e0.record()
-        for _ in range(reps):
-            pos, _, _ = engine.eval_fullrank(*a, k_top)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        out[name] = {"users_per_s": U / (ms * 1e-3), "ms": ms, "fp32_tflops": 2.0 * U * I * d / (ms * 1e-3) / 1e12}
-    out["workload"] = "synthetic yelp-sort shape %d users x %d items d=%d, exact fp32 order-pinned scores" % (U, I, d)
-    out["hr10"] = float((pos < 10).float().mean().item())
+
+    def one(U, I, d, tag, exact_too, reps):
+        g = torch.Generator(device=dev)
+        g.manual_seed(2019)
+        P = torch.randn((U, d), device=dev, generator=g) / d ** 0.5
+        Q = torch.randn((I + 1, d), device=dev, generator=g) / d ** 0.5
+        test = torch.randint(0, I, (U,), device=dev, dtype=torch.int32, generator=g)
+        # exclusion set = 16 random "train" items + the held-out item per user (sorted, unique)
+        tr = torch.randint(0, I, (U, 16), device=dev, dtype=torch.int32, generator=g)
+        rows = torch.cat([tr, test[:, None]], dim=1).cpu().numpy()
+        lists = [np.unique(r) for r in rows]
+        ptr = np.zeros(U + 1, np.int64)
+        ptr[1:] = np.cumsum([x.size for x in lists])
+        idx = np.concatenate(lists).astype(np.int32)
+        t = lambda a, dt: torch.from_numpy(a).to(device=dev, dtype=dt)
+        a = [P, Q, torch.arange(U, device=dev, dtype=torch.int32), test, 0, I, t(ptr, torch.int64), t(idx, torch.int32)]
+        res = {"users": U, "items": I, "d": d}
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, r
+
+        ms, r = timed(lambda: engine.eval_fullrank_tc(*a, check=False)[0])
+        pos_tc = r
+        _, namb = engine.eval_fullrank_tc(*a)
+        issued = 2.0 * U * I * 3 * d / (ms * 1e-3) / 1e12
+        res["tensor_core"] = {"users_per_s": U / (ms * 1e-3), "ms": ms, "ambiguous_pairs_rescored": namb,
+                              "roofline": {"bound": "tensor", "achieved": issued, "peak": tc_peak, "unit": "TFLOP/s",
+                                           "frac": issued / tc_peak, "traffic": None,
+                                           "note": "issued bf16 flops = 3 x useful (hi*hi + hi*lo + lo*hi split); whole "
+                                                   "call incl. operand split, exact re-scoring and exclusion correction"}}
+        if exact_too:
+            ms_e, pos_e = timed(lambda: engine.eval_fullrank(*a, 0, exact=True)[0])
+            res["exact_fp32"] = {"users_per_s": U / (ms_e * 1e-3), "ms": ms_e, "fp32_tflops": 2.0 * U * I * d / (ms_e * 1e-3) / 1e12}
+            res["positions_identical"] = bool(torch.equal(pos_tc, pos_e))
+            ms_k, _ = timed(lambda: engine.eval_fullrank(*a, 10, exact=True)[0])
+            res["exact_fp32_with_top10"] = {"users_per_s": U / (ms_k * 1e-3), "ms": ms_k}
+        res["hr10"] = float((pos_tc < 10).float().mean().item())
+        out[tag] = res
+
+    one(25677, 25815, 128, "yelp_shape_d128", True, 3)
+    one(4096, 10_000_000, 256, "config5_tile_4096_users_x_10M_items_d256", False, 1)
+    out["reference_logs"] = "yelp-sort full-rank eval 250-285 users/s (TF1 CPU, BASELINE.md 1.2)"
     return out
 
 

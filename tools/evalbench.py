@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from apr_b200 import engine
 dev = torch.device('cuda')
 def run(U, I, d, reps=3, exact_too=True):

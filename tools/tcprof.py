@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from apr_b200 import engine
 dev = torch.device('cuda')
 U, I, d = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
