@@ -1,0 +1,72 @@
+"""The Recommender plug-in surface (Recommender.py:3-27) on the CUDA engine."""
+import numpy as np
+import pytest
+
+from oracle import apr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _toy(rng, U=80, I=60):
+    from apr_b200.Dataset import ArrayDataset
+    tu = np.repeat(np.arange(U), 8)
+    ti = np.concatenate([rng.choice(I - 1, 8, replace=False) + 1 for _ in range(U)])
+    return ArrayDataset(tu, ti, np.arange(U), rng.randint(1, I, U))
+
+
+@pytest.mark.parametrize("cls_name", ["BPRRecommender", "FastAdversarialMF"])
+def test_recommender_train_rank_save(cuda_device, tmp_path, cls_name):
+    from apr_b200.FastAdversarialMF import FastAdversarialMF
+    from apr_b200.MFRecommender import BPRRecommender
+    from apr_b200.Recommender import Recommender
+    rng = np.random.RandomState(0)
+    ds = _toy(rng)
+    r = BPRRecommender(ds.num_users, ds.num_items, 16) if cls_name == "BPRRecommender" else \
+        FastAdversarialMF(ds.num_users, ds.num_items, 16, weight=1.0, pop_percent=0.2)
+    assert isinstance(r, Recommender)
+    x, y = r.get_train_instances(ds.trainMatrix)          # ([users, pos, neg], labels)  BPR.py:83-99
+    assert len(x) == 3 and x[0].shape == x[1].shape == x[2].shape == y.shape
+    assert all((int(u), int(j)) not in ds.trainMatrix for u, j in zip(x[0], x[2])) and x[2].min() >= 1
+    P0 = r.mf.embedding_P.cpu().numpy().copy()
+    Q0 = r.mf.embedding_Q.cpu().numpy().copy()
+    loss = r.train(x, y, 64)
+    # oracle on the same instances, batches in order, tail dropped
+    n = (x[0].shape[0] // 64) * 64
+    aP, aQ = np.full_like(P0, 0.1), np.full_like(Q0, 0.1)
+    adver = 1 if cls_name == "FastAdversarialMF" else 0
+    tot = 0.0
+    for s in range(0, n, 64):
+        l, _ = O.loss_acc(P0, Q0, x[0][s:s + 64], x[1][s:s + 64], x[2][s:s + 64])
+        tot += l
+        O.apr_step(P0, Q0, aP, aQ, x[0][s:s + 64], x[1][s:s + 64], x[2][s:s + 64], 0.05, 0.0, 1.0, 0.5, adver)
+    assert abs(loss - tot / n) <= 1e-4 * abs(tot / n)
+    assert np.abs(r.mf.embedding_P.cpu().numpy() - P0).max() <= 2e-4 * np.abs(P0).max()
+    # rank == pinned-order scores of the current tables
+    users = np.array([3, 3, 7, 9], dtype=np.int32)
+    items = np.array([1, 5, 2, 59], dtype=np.int32)
+    got = r.rank(users, items)
+    want = O.score_pairs(r.mf.embedding_P.cpu().numpy(), r.mf.embedding_Q.cpu().numpy(), users, items)
+    assert np.array_equal(np.asarray(got).view(np.uint32), want.view(np.uint32))
+    path = str(tmp_path / "w.npz")
+    r.save(path)
+    r2 = BPRRecommender(ds.num_users, ds.num_items, 16)
+    r2.load_pre_train(path)
+    assert np.array_equal(r2.rank(users, items), got)
+    assert isinstance(r.get_params(), str)
+    if cls_name == "FastAdversarialMF":
+        r.init(x[0], x[1])                                  # FastAdversarialMF.py:83-85,129-145
+        assert len(r.popular_item_x) == int(len(np.unique(x[1])) * 0.2)
+
+
+def test_evaluation_module_batched_on_gpu(cuda_device):
+    from apr_b200 import evaluation
+    from apr_b200.MFRecommender import BPRRecommender
+    rng = np.random.RandomState(1)
+    ds = _toy(rng)
+    r = BPRRecommender(ds.num_users, ds.num_items, 16)
+    P, Q = r.mf.embedding_P.cpu().numpy(), r.mf.embedding_Q.cpu().numpy()
+    test = [ds.testRatings[u][1] for u in range(ds.num_users)]
+    negs = [rng.randint(0, ds.num_items, 99).tolist() for _ in range(ds.num_users)]
+    hits, ndcgs = evaluation.evaluate_model(r, test, negs, 10, 1)      # one launch for all users (rank_batched)
+    ohits, ondcgs = O.evaluate_model_topk(P, Q, {u: test[u] for u in range(1, ds.num_users)}, negs, 10)
+    assert hits == ohits and np.allclose(ndcgs, ondcgs)
