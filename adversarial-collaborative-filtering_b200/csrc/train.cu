@@ -28,6 +28,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -842,8 +843,12 @@ struct AuxStream {
 static AuxStream& aux_stream() {
   static AuxStream a;
   if (!a.ok) {
-    if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaStreamCreateWithFlags(&a.prep_stream, cudaStreamNonBlocking) == cudaSuccess &&
+    // index preparation runs at the LOWEST priority (it only has to stay one sub-chunk ahead: let it fill the gaps the
+    // step kernels leave), the fast-path kernels at the highest
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+        cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming) == cudaSuccess)
@@ -1240,29 +1245,59 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
     APR_LAUNCH_CHECK();
     return APR_OK;
   };
+  // APR_SHARD_TIMING=1: per-stage device times (events) of this call, printed by rank 0 -- diagnosis only
+  static const int timing = env_int("APR_SHARD_TIMING", 0);
+  cudaEvent_t ev[8];
+  float acc_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (timing) for (auto& e : ev) cudaEventCreate(&e);
   for (int s = first_step; s < first_step + count; ++s) {
     int rc;
     APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
     APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
+    if (timing) cudaEventRecord(ev[6], ax.stream);
     rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
                                  ws_bytes, stats, s, 3, ax.stream);
     if (rc) return rc;
     APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+    if (timing) { cudaEventRecord(ev[7], ax.stream); cudaEventRecord(ev[0], st); }
     if (adver) {
       rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
                                    ws_bytes, stats, s, 0, st);
       if (rc) return rc;
+      if (timing) cudaEventRecord(ev[1], st);
       if ((rc = barrier())) return rc;
     }
+    if (timing) cudaEventRecord(ev[2], st);
     rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
                                  ws_bytes, stats, s, 1, st);
     if (rc) return rc;
+    if (timing) cudaEventRecord(ev[3], st);
     if ((rc = barrier())) return rc;
+    if (timing) cudaEventRecord(ev[4], st);
     rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
                                  ws_bytes, stats, s, 2, st);
     if (rc) return rc;
+    if (timing) cudaEventRecord(ev[5], st);
     APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
     if ((rc = barrier())) return rc;
+    if (timing && adver) {
+      cudaStreamSynchronize(st);
+      float t;
+      cudaEventElapsedTime(&t, ev[0], ev[1]); acc_ms[0] += t;   // stage 0
+      cudaEventElapsedTime(&t, ev[1], ev[2]); acc_ms[1] += t;   // barrier
+      cudaEventElapsedTime(&t, ev[2], ev[3]); acc_ms[2] += t;   // stage 1
+      cudaEventElapsedTime(&t, ev[3], ev[4]); acc_ms[3] += t;   // barrier
+      cudaEventElapsedTime(&t, ev[4], ev[5]); acc_ms[4] += t;   // stage 2
+      cudaEventElapsedTime(&t, ev[6], ev[7]); acc_ms[5] += t;   // fast kernel (second stream)
+      cudaEventElapsedTime(&t, ev[0], ev[5]); acc_ms[6] += t;   // general path total
+    }
+  }
+  if (timing) {
+    if (rank == 0 && adver)
+      fprintf(stderr, "[shard timing] per step (us): stage0 %.1f  bar %.1f  stage1 %.1f  bar %.1f  stage2 %.1f | fast %.1f | general total %.1f\n",
+              1e3 * acc_ms[0] / count, 1e3 * acc_ms[1] / count, 1e3 * acc_ms[2] / count, 1e3 * acc_ms[3] / count,
+              1e3 * acc_ms[4] / count, 1e3 * acc_ms[5] / count, 1e3 * acc_ms[6] / count);
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   return APR_OK;
 }

@@ -395,8 +395,10 @@ def main_single(args):
         bytes_total += float(16 * d * cnt.sum() + 12 * B * c[0].shape[0])
     achieved = bytes_total / (ms_run * 1e-3) / 1e9
     steps_roof = sum(c[0].shape[0] for c in chunks[:n_roof])
+    # traffic: dram__bytes_read+write per step from the ncu capture of this command (profiles/r1f_launches_mode0_B65536.csv:
+    # fast_kernel 177+116 MB, 3 general stages ~16 MB each; serialised cold-cache replay, late write-backs not attributed)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_kind": peak_kind,
+                "traffic": 340.7e6 if (B == 65536 and d == 128 and args.mode == 0) else None, "peak_kind": peak_kind,
                 "kernel": "step_persistent_kernel<32,1,true>" if args.mode == 1 else "fast_kernel<32,1,true> || 3 x general_stage_kernel<32,1> per step",
                 "bytes_per_step_model": bytes_total / steps_roof, "ms_per_step_kernel": ms_run / steps_roof}
 
