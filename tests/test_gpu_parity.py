@@ -313,3 +313,49 @@ def test_row_sharded_step_matches_oracle_emulated_ranks(cuda_device, world, adve
     _close(t.gather_full("accQ", I).cpu().numpy(), raQ)
     for r in range(world):  # shared-item workspace shards back to zero
         assert int(t.local("GQ", r).count_nonzero().item()) == 0 and int(t.local("HQ", r).count_nonzero().item()) == 0
+
+
+@pytest.mark.timeout(900)
+def test_full_size_config4_step_matches_oracle_on_touched_rows(cuda_device):
+    """BASELINE.json configs[3] at FULL size (10M users x 2M items, d=128, 65 536 triples per step): two APR steps on the
+    GPU; every row they touch is gathered and compared with the oracle run on those rows; untouched rows must be
+    bit-identical to what they were (checksum of a strided sample)."""
+    from apr_b200 import engine
+    dev = cuda_device
+    if torch.cuda.get_device_properties(dev).total_memory < 40e9:
+        pytest.skip("needs ~13 GB of device memory")
+    U, I, d, S, B = 10_000_000, 2_000_000, 128, 2, 65536
+    P = torch.empty((U, d), device=dev)
+    Q = torch.empty((I, d), device=dev)
+    engine.init_truncated_normal(P, 0.01, 2019, 0)
+    engine.init_truncated_normal(Q, 0.01, 2019, 1)
+    aP, aQ = torch.full_like(P, 0.1), torch.full_like(Q, 0.1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    u = torch.randint(0, U, (S, B), device=dev, dtype=torch.int32, generator=g)
+    i = torch.randint(0, I, (S, B), device=dev, dtype=torch.int32, generator=g)
+    j = torch.randint(0, I, (S, B), device=dev, dtype=torch.int32, generator=g)
+    uu = torch.unique(u.flatten().long())
+    ii = torch.unique(torch.cat([i.flatten(), j.flatten()]).long())
+    P0, Q0 = P[uu].cpu().numpy(), Q[ii].cpu().numpy()
+    sample_p = torch.arange(0, U, 997, device=dev)
+    mask = ~torch.isin(sample_p, uu)
+    before = P[sample_p[mask]].clone()
+    ws = engine.TrainWorkspace(S, B, d, dev)
+    engine.train_steps(P, Q, aP, aQ, u, i, j, 0.05, 0.0, 1.0, 0.5, 1, ws)
+    torch.cuda.synchronize()
+    # oracle on the compact tables of touched rows
+    un, inn, jn = u.cpu().numpy(), i.cpu().numpy(), j.cpu().numpy()
+    uun, iin = uu.cpu().numpy(), ii.cpu().numpy()
+    raP, raQ = np.full_like(P0, 0.1), np.full_like(Q0, 0.1)
+    for s in range(S):
+        O.apr_step(P0, Q0, raP, raQ, np.searchsorted(uun, un[s]), np.searchsorted(iin, inn[s]), np.searchsorted(iin, jn[s]),
+                   0.05, 0.0, 1.0, 0.5, 1)
+    _close(P[uu].cpu().numpy(), P0)
+    _close(Q[ii].cpu().numpy(), Q0)
+    _close(aP[uu].cpu().numpy(), raP)
+    _close(aQ[ii].cpu().numpy(), raQ)
+    assert torch.equal(P[sample_p[mask]], before)                  # untouched rows untouched
+    cnt = ws.unique_counts(S)
+    assert cnt[:, 0].sum() == sum(np.unique(un[s]).size for s in range(S))
+    assert cnt[:, 1].sum() == sum(np.unique(np.concatenate([inn[s], jn[s]])).size for s in range(S))
