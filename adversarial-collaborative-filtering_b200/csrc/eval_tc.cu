@@ -29,7 +29,8 @@ namespace apr {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_KC = 64;
 constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16)
-constexpr int TC_NORM_BYTES = 512;         // 128 fp32 norms per item tile
+constexpr int TC_NORM_BYTES = 528;         // per item tile: 128 fp32 norms + the 4 maxima of its 32-column blocks
+constexpr int TC_NORM_FLOATS = TC_NORM_BYTES / 4;
 constexpr int TC_NORM_SLOTS = 8;         // smem ring of item-norm blocks (0 slots: the epilogue reads them from global)
 constexpr int TC_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 // capacity of the ambiguous list: max(256, n_items / 256) pairs per user (~0.4 % of all pairs; ~0.07-0.2 % are expected)
@@ -99,6 +100,16 @@ tc_prep_kernel(const float* __restrict__ T, int d, const int32_t* __restrict__ r
   }
 }
 
+// per item tile: maxima of the norms of its four 32-column blocks, stored behind the 128 norms
+__global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles, int nchunk, int64_t tile_bytes) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles * 4) return;
+  float* nb = reinterpret_cast<float*>(img + int64_t(t >> 2) * tile_bytes + int64_t(nchunk) * TC_CHUNK_BYTES);
+  float m = 0.f;
+  for (int k = 0; k < 32; ++k) m = fmaxf(m, nb[(t & 3) * 32 + k]);
+  nb[128 + (t & 3)] = m;
+}
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -131,6 +142,17 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {   // true in exactly one lane of a converged warp (same lane every time)
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_bf16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -178,12 +200,14 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
                 int32_t* __restrict__ position, int2* __restrict__ amb, int* __restrict__ amb_count, int amb_cap,
                 int* __restrict__ err) {
   extern __shared__ unsigned char smem_raw[];
+  __shared__ int s_amb_count;   // fill of this CTA's ambiguous-list segment (shared-memory atomic: no global round trip
+                                // on the epilogue's critical path); published to amb_count[cta] when the CTA finishes
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align by hand (the launch reserves the slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;                                        // nchunk x 16 KB
   unsigned char* sB = sA + size_t(nchunk) * TC_CHUNK_BYTES;        // nstage x 16 KB
   float* sNorm = reinterpret_cast<float*>(sB + size_t(nstage) * TC_CHUNK_BYTES);  // norm_slots x 128 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + norm_slots * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + norm_slots * TC_NORM_FLOATS + 2);  // 8-byte aligned
   // bars: [0,nstage) full, [nstage,2nstage) empty, then tfull[2], tempty[2], afull, nfull[norm_slots]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * nstage + 5 + norm_slots);
   const uint32_t bar0 = smem_u32(bars);
@@ -201,6 +225,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   const int ntile = max(0, t_end - t_begin);
 
   if (threadIdx.x == 0) {
+    s_amb_count = 0;
     for (int s = 0; s < nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_THREADS - 64); }
     mbar_init(afull_bar, 1);
@@ -236,7 +261,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
             // the item norms ride on their OWN barrier: the epilogue threads acquire it themselves before reading.
             // (slot reuse is safe: the producer is never more than nstage/nchunk + 2 < norm_slots tiles ahead)
             mbar_expect_tx(nfull_bar(t % norm_slots), TC_NORM_BYTES);
-            bulk_g2s(smem_u32(sNorm + (t % norm_slots) * 128), bsrc + size_t(nchunk) * TC_CHUNK_BYTES, TC_NORM_BYTES,
+            bulk_g2s(smem_u32(sNorm + (t % norm_slots) * TC_NORM_FLOATS), bsrc + size_t(nchunk) * TC_CHUNK_BYTES, TC_NORM_BYTES,
                      nfull_bar(t % norm_slots));
           }
           if (++stage == nstage) { stage = 0; phase ^= 1u; }
@@ -244,37 +269,46 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: a single thread drives the tensor core =====
-    if (lane == 0 && ntile > 0) {
-      bool ok = mbar_wait(afull_bar, 0, err);
+    // ===== MMA issuer.  The whole warp walks the pipeline convergently (every lane polls the mbarriers, which keeps
+    // all loop state warp-uniform); the tcgen05 instructions themselves go out from the one lane elect.sync picks.
+    // Written this way ptxas keeps descriptors in uniform registers and emits bare UTCHMMAs; a `lane == 0` branch
+    // instead wraps every MMA in an ELECT/BRA.U.ANY loop (~180 issue cycles per 64-cycle MMA, profiles/r1h). =====
+    if (ntile > 0) {
+      bool ok = __all_sync(0xffffffffu, mbar_wait(afull_bar, 0, err));
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
+      constexpr uint64_t kChunkStep = TC_CHUNK_BYTES >> 4;   // descriptor address field counts 16-byte units
       for (int t = 0; t < ntile && ok; ++t) {
         const int buf = t & 1;
-        ok = mbar_wait(tempty_bar(buf), ((t >> 1) & 1u) ^ 1u, err);
+        ok = __all_sync(0xffffffffu, mbar_wait(tempty_bar(buf), ((t >> 1) & 1u) ^ 1u, err));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * TC_BN);
         for (int c = 0; c < nchunk && ok; ++c) {
-          ok = mbar_wait(full_bar(stage), phase, err);
+          ok = __all_sync(0xffffffffu, mbar_wait(full_bar(stage), phase, err));
           tc_fence_after();
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + size_t(stage) * TC_CHUNK_BYTES));
-          // A chunk(s) this B chunk meets: K'=3d layout -> chunk c; split2 -> b_hi[cc] x {a_hi[cc], a_lo[cc]}, b_lo[cc] x a_hi[cc]
-          const int a0 = cps ? (c % cps) : c;
-          const int a1 = (cps && c < cps) ? cps + c : -1;
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + size_t(a0) * TC_CHUNK_BYTES));
+          if (ok && elect_one()) {
+            const uint64_t bdesc = bdesc0 + uint64_t(stage) * kChunkStep;
+            // A chunk(s) this B chunk meets: K'=3d layout -> chunk c; split2 -> b_hi[cc] x {a_hi[cc], a_lo[cc]}, b_lo[cc] x a_hi[cc]
+            const int a0 = (cps && c >= cps) ? c - cps : c;
+            const uint64_t adesc = adesc0 + uint64_t(a0) * kChunkStep;
+            tc_mma_bf16(tmem_d, adesc, bdesc, kIdescBf16M128N128, c ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
-            tc_mma_bf16(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128, (c | k) ? 1u : 0u);
-          if (a1 >= 0) {
-            const uint64_t adesc1 = umma_desc_sw128(smem_u32(sA + size_t(a1) * TC_CHUNK_BYTES));
+            for (int k = 1; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
+              tc_mma_bf16_acc(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
+            if (cps && c < cps) {
+              const uint64_t adesc1 = adesc + uint64_t(cps) * kChunkStep;
 #pragma unroll
-            for (int k = 0; k < TC_KC / 16; ++k)
-              tc_mma_bf16(tmem_d, adesc1 + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128, 1u);
+              for (int k = 0; k < TC_KC / 16; ++k)
+                tc_mma_bf16_acc(tmem_d, adesc1 + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
+            }
+            tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+            if (c == nchunk - 1) tc_commit(tfull_bar(buf));   // accumulator of this tile complete
           }
-          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(buf));      // accumulator of this tile complete
       }
     }
   } else {
@@ -289,8 +323,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
     const float sp = uvalid ? spos[uidx] : CUDART_INF_F;
     const float gu = uvalid ? user_scale[uidx] : 0.f;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    int* my_count = amb_count + cta;                       // amb_cap = capacity of ONE CTA's segment
-    int2* my_amb = amb + int64_t(cta) * amb_cap;
+    int2* my_amb = amb + int64_t(cta) * amb_cap;           // amb_cap = capacity of ONE CTA's segment
     int cnt = 0;
     bool ok = true;
     for (int t = 0; t < ntile && ok; ++t) {
@@ -298,7 +331,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
       ok = mbar_wait(tfull_bar(buf), (t >> 1) & 1u, err);
       tc_fence_after();
       if (norm_slots && ok) ok = mbar_wait(nfull_bar(t % norm_slots), uint32_t(t / norm_slots) & 1u, err);
-      const float* qn = norm_slots ? sNorm + (t % norm_slots) * 128
+      const float* qn = norm_slots ? sNorm + (t % norm_slots) * TC_NORM_FLOATS
                                    : reinterpret_cast<const float*>(b_img + int64_t(t_begin + t) * tile_bytes +
                                                                     int64_t(nchunk) * TC_CHUNK_BYTES);
       const int n0 = item_lo + (t_begin + t) * TC_BN;
@@ -307,29 +340,26 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         const int col0 = half * 64 + cc * 32;
         float v[32];
         tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_BN + col0), v);
-        unsigned hi_mask = 0u, in_mask = 0u;   // bit j: v > sp + e   /   v >= sp - e
+        // block-level conservative band: e_max = gamma ||p|| * max ||q|| over the block's 32 columns, so both
+        // thresholds are constants of the block and a score costs two compares + two predicated bit-sets:
+        //   v >  sp + e_max -> certainly counted      v < sp - e_max -> certainly not      else -> ambiguous list
+        // (the list is re-scored exactly afterwards, so a slightly wide band only costs a few more list entries)
+        const float emax = gu * qn[128 + (col0 >> 5)];
+        const float thi = sp + emax, tlo = sp - emax;
+        unsigned hi_mask = 0u, in_mask = 0u;   // bit j: v > thi   /   v >= tlo
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 q4 = *reinterpret_cast<const float4*>(qn + col0 + 4 * j4);
-          const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int jx = 4 * j4 + k;
-            const float e = gu * qv[k];
-            hi_mask |= (v[jx] > sp + e) ? (1u << jx) : 0u;
-            in_mask |= (v[jx] >= sp - e) ? (1u << jx) : 0u;
-          }
+        for (int jx = 0; jx < 32; ++jx) {
+          hi_mask |= (v[jx] > thi) ? (1u << jx) : 0u;
+          in_mask |= (v[jx] >= tlo) ? (1u << jx) : 0u;
         }
-        // columns past item_hi (padding of the last tile) never count
-        const int ncols = min(32, max(0, item_hi - (n0 + col0)));
-        const unsigned colmask = ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u);
-        hi_mask &= colmask;
-        cnt += __popc(hi_mask);
-        unsigned amb_bits = uvalid ? (in_mask & ~hi_mask & colmask) : 0u;
-        while (amb_bits) {
-          const int jx = __ffs(amb_bits) - 1;
-          amb_bits &= amb_bits - 1;
-          const int slot = atomicAdd(my_count, 1);  // per-CTA counter: no chip-wide same-address serialisation
+        const int ncols = item_hi - (n0 + col0);   // columns past item_hi (tile padding) never count
+        const unsigned valid = !uvalid || ncols <= 0 ? 0u : (ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u));
+        cnt += __popc(hi_mask & valid);
+        unsigned amb = in_mask & ~hi_mask & valid;
+        while (amb) {                           // rare: ~0.1% of the scores
+          const int jx = __ffs(amb) - 1;
+          amb &= amb - 1;
+          const int slot = atomicAdd(&s_amb_count, 1);
           if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
         }
       }
@@ -340,6 +370,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) amb_count[blockIdx.y * gridDim.x + blockIdx.x] = s_amb_count;
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
@@ -437,6 +468,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
       P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, L.split2, gamma, a_img, uscale);
   tc_prep_kernel<<<grid_for(int64_t(W.n_itiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
       Q, d, nullptr, item_lo, n_items, L.nchunk, L.tile_bytes, 0, L.split2, gamma, b_img, nullptr);
+  tc_norm_max_kernel<<<(W.n_itiles * 4 + 255) / 256, 256, 0, st>>>(b_img, W.n_itiles, L.nchunk, L.tile_bytes);
   APR_LAUNCH_CHECK();
 
   // shared memory: 1024 alignment slack + A image + B stages + (optional) norm ring + barriers
