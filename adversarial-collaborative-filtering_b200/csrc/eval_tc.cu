@@ -32,7 +32,9 @@ constexpr int TC_CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B (64 bf16)
 constexpr int TC_NORM_BYTES = 528;         // per item tile: 128 fp32 norms + the 4 maxima of its 32-column blocks
 constexpr int TC_NORM_FLOATS = TC_NORM_BYTES / 4;
 constexpr int TC_NORM_SLOTS = 8;         // smem ring of item-norm blocks (0 slots: the epilogue reads them from global)
-constexpr int TC_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int TC_THREADS = 576;            // warps 0-15 epilogue (four per TMEM lane quarter), warp 16 TMA producer, warp 17 MMA
+constexpr int TC_PRODUCER_WARP = 16;
+constexpr int TC_MMA_WARP = 17;            // highest warp id: the scheduler favours it, and MMA issue is the critical chain
 // capacity of the ambiguous list: max(256, n_items / 256) pairs per user (~0.4 % of all pairs; ~0.07-0.2 % are expected)
 static inline int64_t tc_amb_cap(int n_users, int n_items) {
   return std::min<int64_t>(int64_t(n_users) * std::max(256, n_items / 256), 0x7fffff00);
@@ -106,7 +108,10 @@ __global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles,
   if (t >= n_tiles * 4) return;
   float* nb = reinterpret_cast<float*>(img + int64_t(t >> 2) * tile_bytes + int64_t(nchunk) * TC_CHUNK_BYTES);
   float m = 0.f;
-  for (int k = 0; k < 32; ++k) m = fmaxf(m, nb[(t & 3) * 32 + k]);
+  for (int k = 0; k < 32; ++k) {
+    const float x = nb[(t & 3) * 32 + k];
+    m = (x < CUDART_INF_F) ? fmaxf(m, x) : CUDART_INF_F;   // NaN / Inf norms poison the block maximum on purpose
+  }
   nb[128 + (t & 3)] = m;
 }
 
@@ -142,6 +147,11 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned mad_hi_u32(unsigned a, unsigned b, unsigned c) {   // hi32(a * b) + c, on the FMA pipe
+  unsigned d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
 }
 __device__ __forceinline__ bool elect_one() {   // true in exactly one lane of a converged warp (same lane every time)
   uint32_t pred;
@@ -193,12 +203,17 @@ constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((T
 // ------------------------------------------------------------------------------------------------
 // the GEMM + counting kernel
 // ------------------------------------------------------------------------------------------------
+// NCHUNK / CPS > 0: the chunk layout is a compile-time constant (d = 64, 128, 256) and the MMA issue loop unrolls into
+// straight-line code with constant A-descriptor offsets; NCHUNK == 0 is the generic (runtime layout) instantiation.
+template <int NCHUNK, int CPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int nchunk,
-                int64_t tile_bytes, int nstage, int norm_slots, int cps, int n_users, const float* __restrict__ spos,
+tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int nchunk_rt,
+                int64_t tile_bytes, int nstage, int norm_slots, int cps_rt, int n_users, const float* __restrict__ spos,
                 const float* __restrict__ user_scale, int item_lo, int item_hi, int tiles_total, int tiles_per_cta,
                 int32_t* __restrict__ position, int2* __restrict__ amb, int* __restrict__ amb_count, int amb_cap,
                 int* __restrict__ err) {
+  const int nchunk = NCHUNK ? NCHUNK : nchunk_rt;
+  const int cps = NCHUNK ? CPS : cps_rt;
   extern __shared__ unsigned char smem_raw[];
   __shared__ int s_amb_count;   // fill of this CTA's ambiguous-list segment (shared-memory atomic: no global round trip
                                 // on the epilogue's critical path); published to amb_count[cta] when the CTA finishes
@@ -232,7 +247,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
     for (int k = 0; k < norm_slots; ++k) mbar_init(nfull_bar(k), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -241,7 +256,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == TC_PRODUCER_WARP) {
     // ===== producer: one lane streams the pre-swizzled images through the TMA engine =====
     if (lane == 0 && ntile > 0) {
       mbar_expect_tx(afull_bar, uint32_t(nchunk) * TC_CHUNK_BYTES);
@@ -268,55 +283,54 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer.  The whole warp walks the pipeline convergently (every lane polls the mbarriers, which keeps
-    // all loop state warp-uniform); the tcgen05 instructions themselves go out from the one lane elect.sync picks.
-    // Written this way ptxas keeps descriptors in uniform registers and emits bare UTCHMMAs; a `lane == 0` branch
-    // instead wraps every MMA in an ELECT/BRA.U.ANY loop (~180 issue cycles per 64-cycle MMA, profiles/r1h). =====
-    if (ntile > 0) {
-      bool ok = __all_sync(0xffffffffu, mbar_wait(afull_bar, 0, err));
+  } else if (warp == TC_MMA_WARP) {
+    // ===== MMA issuer: the one lane elect.sync picks walks the pipeline and feeds the tensor core.  Its instruction
+    // stream IS the critical chain of this kernel (profiles/README.md, r1h-r1j): ptxas keeps the descriptors in uniform
+    // registers and emits bare UTCHMMAs only when the lane comes from elect.sync (a `lane == 0` branch wraps every MMA
+    // in an ELECT/BRA.U.ANY loop), and the compile-time chunk layout removes the scalar bookkeeping between them. =====
+    if (ntile > 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
       constexpr uint64_t kChunkStep = TC_CHUNK_BYTES >> 4;   // descriptor address field counts 16-byte units
+      bool ok = mbar_wait(afull_bar, 0, err);
       for (int t = 0; t < ntile && ok; ++t) {
         const int buf = t & 1;
-        ok = __all_sync(0xffffffffu, mbar_wait(tempty_bar(buf), ((t >> 1) & 1u) ^ 1u, err));
+        if (!mbar_wait(tempty_bar(buf), ((t >> 1) & 1u) ^ 1u, err)) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(buf * TC_BN);
-        for (int c = 0; c < nchunk && ok; ++c) {
-          ok = __all_sync(0xffffffffu, mbar_wait(full_bar(stage), phase, err));
+#pragma unroll
+        for (int c = 0; c < nchunk; ++c) {
+          if (!mbar_wait(full_bar(stage), phase, err)) { ok = false; break; }
           tc_fence_after();
-          if (ok && elect_one()) {
-            const uint64_t bdesc = bdesc0 + uint64_t(stage) * kChunkStep;
-            // A chunk(s) this B chunk meets: K'=3d layout -> chunk c; split2 -> b_hi[cc] x {a_hi[cc], a_lo[cc]}, b_lo[cc] x a_hi[cc]
-            const int a0 = (cps && c >= cps) ? c - cps : c;
-            const uint64_t adesc = adesc0 + uint64_t(a0) * kChunkStep;
-            tc_mma_bf16(tmem_d, adesc, bdesc, kIdescBf16M128N128, c ? 1u : 0u);
+          const uint64_t bdesc = bdesc0 + uint64_t(stage) * kChunkStep;
+          // A chunk(s) this B chunk meets: K'=3d layout -> chunk c; split2 -> b_hi[cc] x {a_hi[cc], a_lo[cc]}, b_lo[cc] x a_hi[cc]
+          const int a0 = (cps && c >= cps) ? c - cps : c;
+          const uint64_t adesc = adesc0 + uint64_t(a0) * kChunkStep;
+          tc_mma_bf16(tmem_d, adesc, bdesc, kIdescBf16M128N128, c ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
-              tc_mma_bf16_acc(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
-            if (cps && c < cps) {
-              const uint64_t adesc1 = adesc + uint64_t(cps) * kChunkStep;
+          for (int k = 1; k < TC_KC / 16; ++k)  // K = 16 per instruction: +32 bytes inside the swizzle atom
+            tc_mma_bf16_acc(tmem_d, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
+          if (cps && c < cps) {
+            const uint64_t adesc1 = adesc + uint64_t(cps) * kChunkStep;
 #pragma unroll
-              for (int k = 0; k < TC_KC / 16; ++k)
-                tc_mma_bf16_acc(tmem_d, adesc1 + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
-            }
-            tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-            if (c == nchunk - 1) tc_commit(tfull_bar(buf));   // accumulator of this tile complete
+            for (int k = 0; k < TC_KC / 16; ++k)
+              tc_mma_bf16_acc(tmem_d, adesc1 + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdescBf16M128N128);
           }
-          __syncwarp();
+          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (c == nchunk - 1) tc_commit(tfull_bar(buf));   // accumulator of this tile complete
           if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
       }
     }
+    __syncwarp();
   } else {
-    // ===== epilogue: TMEM -> registers.  Thread = one user row x one half (64) of the tile's columns. =====
+    // ===== epilogue: TMEM -> registers.  Thread = one user row x one 32-column block of the tile. =====
     // Branch-free per element: two threshold compares folded into bit masks; the count is a popcount, the (rare)
     // ambiguous bits take a slow path after each 32-column block.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which 64 columns of the tile
+    const int col0 = (warp >> 2) * 32;            // which 32 columns of the tile
     const int m = quarter * 32 + lane;
     const int uidx = m0 + m;
     const bool uvalid = uidx < n_users;
@@ -326,41 +340,65 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
     int2* my_amb = amb + int64_t(cta) * amb_cap;           // amb_cap = capacity of ONE CTA's segment
     int cnt = 0;
     bool ok = true;
+    int nslot = 0;          // norm ring position of tile t (t % norm_slots) and its phase, kept without dividing
+    uint32_t nphase = 0;
     for (int t = 0; t < ntile && ok; ++t) {
       const int buf = t & 1;
       ok = mbar_wait(tfull_bar(buf), (t >> 1) & 1u, err);
       tc_fence_after();
-      if (norm_slots && ok) ok = mbar_wait(nfull_bar(t % norm_slots), uint32_t(t / norm_slots) & 1u, err);
-      const float* qn = norm_slots ? sNorm + (t % norm_slots) * TC_NORM_FLOATS
+      if (norm_slots && ok) ok = mbar_wait(nfull_bar(nslot), nphase, err);
+      const float* qn = norm_slots ? sNorm + nslot * TC_NORM_FLOATS
                                    : reinterpret_cast<const float*>(b_img + int64_t(t_begin + t) * tile_bytes +
                                                                     int64_t(nchunk) * TC_CHUNK_BYTES);
+      if (++nslot >= norm_slots) { nslot = 0; nphase ^= 1u; }
       const int n0 = item_lo + (t_begin + t) * TC_BN;
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = half * 64 + cc * 32;
+      {
         float v[32];
         tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * TC_BN + col0), v);
-        // block-level conservative band: e_max = gamma ||p|| * max ||q|| over the block's 32 columns, so both
-        // thresholds are constants of the block and a score costs two compares + two predicated bit-sets:
-        //   v >  sp + e_max -> certainly counted      v < sp - e_max -> certainly not      else -> ambiguous list
-        // (the list is re-scored exactly afterwards, so a slightly wide band only costs a few more list entries)
-        const float emax = gu * qn[128 + (col0 >> 5)];
-        const float thi = sp + emax, tlo = sp - emax;
-        unsigned hi_mask = 0u, in_mask = 0u;   // bit j: v > thi   /   v >= tlo
+        // Block-level conservative band.  With w = fl(v - sp) and E >= gamma ||p|| max_block ||q|| (+ the rounding of w):
+        //     w >  E  -> the exact score certainly beats the held-out item: counted here
+        //     w < -E  -> certainly does not
+        //     |w| <= E -> undecidable from the bf16x3 product: (user, item) goes to the ambiguous list, re-scored exactly
+        // The tile's 16K scores make this loop the kernel's second critical resource after the tensor pipe, and compare/
+        // select/add all issue on the ALU pipe (one warp instruction per 2 cycles per scheduler).  So the count is taken
+        // on the FMA pipe instead -- sign bit of (E - w), summed with mad.hi -- and the band test is ONE min per score;
+        // only a group of 8 columns that has a score inside the band is looked at element by element.
+        float E = fmaf(gu * qn[128 + (col0 >> 5)], 1.0f + 0x1p-21f, 1e-30f);
+        if (!(E < CUDART_INF_F)) E = CUDART_INF_F;        // non-finite norms: everything undecidable -> exact re-score
+        const int ncols = item_hi - (n0 + col0);           // columns past item_hi (padding of the last tile) never count
+        if (ncols >= 32) {
+          unsigned c = 0u;
+          float mg[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
 #pragma unroll
-        for (int jx = 0; jx < 32; ++jx) {
-          hi_mask |= (v[jx] > thi) ? (1u << jx) : 0u;
-          in_mask |= (v[jx] >= tlo) ? (1u << jx) : 0u;
-        }
-        const int ncols = item_hi - (n0 + col0);   // columns past item_hi (tile padding) never count
-        const unsigned valid = !uvalid || ncols <= 0 ? 0u : (ncols >= 32 ? 0xffffffffu : ((1u << ncols) - 1u));
-        cnt += __popc(hi_mask & valid);
-        unsigned amb = in_mask & ~hi_mask & valid;
-        while (amb) {                           // rare: ~0.1% of the scores
-          const int jx = __ffs(amb) - 1;
-          amb &= amb - 1;
-          const int slot = atomicAdd(&s_amb_count, 1);
-          if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
+          for (int jx = 0; jx < 32; ++jx) {
+            const float w = v[jx] - sp;
+            c = mad_hi_u32(__float_as_uint(E - w), 2u, c);  // += (w > E); E - w is never -0
+            mg[jx >> 3] = fminf(mg[jx >> 3], fabsf(w));
+          }
+          cnt += int(c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (mg[g] <= E && uvalid) {                     // ~0.1% of the scores land in the band
+#pragma unroll
+              for (int jx = 8 * g; jx < 8 * g + 8; ++jx) {
+                if (fabsf(v[jx] - sp) <= E) {
+                  const int slot = atomicAdd(&s_amb_count, 1);
+                  if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
+                }
+              }
+            }
+          }
+        } else if (ncols > 0 && uvalid) {                   // ragged last block of the item range
+#pragma unroll
+          for (int jx = 0; jx < 32; ++jx) {
+            if (jx >= ncols) continue;
+            const float w = v[jx] - sp;
+            if (w > E) ++cnt;
+            else if (fabsf(w) <= E) {
+              const int slot = atomicAdd(&s_amb_count, 1);
+              if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -371,7 +409,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) amb_count[blockIdx.y * gridDim.x + blockIdx.x] = s_amb_count;
-  if (warp == 1) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
@@ -480,7 +518,6 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   int nstage = int((max_smem - fixed_smem - size_t(norm_slots) * TC_NORM_BYTES) / TC_CHUNK_BYTES);
   nstage = std::max(1, std::min(nstage, 8));
   const size_t smem = fixed_smem + size_t(norm_slots) * TC_NORM_BYTES + size_t(nstage) * TC_CHUNK_BYTES;
-  APR_CUDA_CHECK(cudaFuncSetAttribute(tc_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   // one CTA per SM (TMEM + shared memory): split the item tiles so that the CTAs fill whole waves of SMs, with as few
   // splits as reach >= 92 % wave efficiency and >= 8 item tiles per CTA (amortises the A image and the pipeline fill)
   int splits = 1;
@@ -503,9 +540,21 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   if (cap_cta < 16) return APR_E_UNSUPPORTED;
   const int32_t meta[2] = {n_ctas, cap_cta};
   APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
-  tc_count_kernel<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, L.split2 ? L.cps : 0, n_users,
+  {
+    cudaError_t attr_err = cudaSuccess;
+    auto launch = [&](auto kern) {
+      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (attr_err == cudaSuccess) kern<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, L.split2 ? L.cps : 0, n_users,
                                                                       spos, uscale, item_lo, item_hi, W.n_itiles, per,
                                                                       position, amb, amb_count, cap_cta, err_flag);
+    };
+    const int cps_arg = L.split2 ? L.cps : 0;
+    if (L.nchunk == 4 && cps_arg == 2) launch(tc_count_kernel<4, 2>);        // d = 128
+    else if (L.nchunk == 8 && cps_arg == 4) launch(tc_count_kernel<8, 4>);   // d = 256
+    else if (L.nchunk == 2 && cps_arg == 1) launch(tc_count_kernel<2, 1>);   // d = 64
+    else launch(tc_count_kernel<0, 0>);
+    APR_CUDA_CHECK(attr_err);
+  }
   APR_LAUNCH_CHECK();
   tc_rescore_kernel<<<dim3(std::max(1, std::min(64, cap_cta / 256 + 1)), n_ctas), 256, 0, st>>>(P, Q, d, users, spos, amb,
                                                                                               amb_count, cap_cta, position);
