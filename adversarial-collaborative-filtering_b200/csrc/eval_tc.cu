@@ -102,6 +102,48 @@ tc_prep_kernel(const float* __restrict__ T, int d, const int32_t* __restrict__ r
   }
 }
 
+// split2 layouts with d = 8 * TPR, TPR in {8, 16, 32}: one thread per (row, 8 source elements) reads its 32 bytes ONCE and
+// writes both the hi piece and the lo piece; the TPR lanes of a row sit in one warp and reduce the row norm by shuffles.
+// (the generic kernel above reads every element twice and walks the row a third time for the norm)
+template <int TPR>
+__global__ void __launch_bounds__(256)
+tc_prep_split2_kernel(const float* __restrict__ T, const int32_t* __restrict__ row_ids, int row_lo, int n_rows,
+                      int64_t tile_bytes, int is_a, float gamma, unsigned char* __restrict__ img,
+                      float* __restrict__ user_scale) {
+  constexpr int d = TPR * 8, cps = TPR / 8, nchunk = 2 * cps;
+  const int64_t total = int64_t((n_rows + 127) / 128) * 128 * TPR;   // multiple of 32: warps stay whole
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t rr = t / TPR;
+    const int pc = int(t) & (TPR - 1);
+    const int tile = int(rr >> 7), r = int(rr & 127);
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rr < n_rows) {
+      const int64_t src_row = row_ids ? int64_t(row_ids[rr]) : int64_t(row_lo) + rr;
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + pc * 8));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(T + src_row * d + pc * 8 + 4));
+      x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+    }
+    __nv_bfloat16 hi[8], lo[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = __float2bfloat16_rn(x[e]);
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
+      ss = fmaf(x[e], x[e], ss);
+    }
+    unsigned char* dst = img + int64_t(tile) * tile_bytes + int64_t(pc >> 3) * TC_CHUNK_BYTES + r * 128 + (((pc & 7) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + int64_t(cps) * TC_CHUNK_BYTES) = *reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (pc == 0) {
+      const float nrm = sqrtf(ss) * 1.0001f;
+      if (is_a) { if (rr < n_rows) user_scale[rr] = gamma * nrm * 1.0001f; }
+      else *reinterpret_cast<float*>(img + int64_t(tile) * tile_bytes + int64_t(nchunk) * TC_CHUNK_BYTES + r * 4) = nrm;
+    }
+  }
+}
+
 // per item tile: maxima of the norms of its four 32-column blocks, stored behind the 128 norms
 __global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles, int nchunk, int64_t tile_bytes) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,6 +457,52 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   }
 }
 
+// exact re-scoring, shared-memory variant: every pair of a list segment belongs to ONE user tile (the producing CTA's),
+// so the block stages those 128 rows of P once (row stride d + 4 floats: quarter-warp LDS.128 of distinct rows spread
+// over the banks) and only the item rows travel per pair.  Halves the L2 traffic the plain variant is bound by.
+__global__ void __launch_bounds__(512)
+tc_rescore_tile_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
+                       int n_users, int n_utiles, const float* __restrict__ spos, const int2* __restrict__ amb,
+                       const int* __restrict__ amb_count, int amb_cap, int32_t* __restrict__ position) {
+  extern __shared__ float4 sP4[];
+  const int seg = blockIdx.y;
+  const int n = min(amb_count[seg], amb_cap);
+  if (int(blockIdx.x * blockDim.x) >= n) return;
+  const int m0 = (seg % n_utiles) * TC_BM;
+  const int d4 = d >> 2, stride4 = d4 + 1;
+  for (int idx = threadIdx.x; idx < TC_BM * d4; idx += blockDim.x) {
+    const int r = idx / d4, c = idx - r * d4;
+    const int uidx = m0 + r;
+    sP4[r * stride4 + c] = uidx < n_users ? __ldg(reinterpret_cast<const float4*>(P + int64_t(users[uidx]) * d) + c)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int2* list = amb + int64_t(seg) * amb_cap;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int2 a = list[t];
+    const float4* p4 = sP4 + (a.x - m0) * stride4;
+    const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
+    float acc = 0.f;
+    int e = 0;
+    for (; e + 8 <= d4; e += 8) {   // a whole 128-byte line of the item row in flight at once, consumed in k order
+      float4 y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = __ldg(q4 + e + k);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 x = p4[e + k];
+        acc = fmaf(x.x, y[k].x, acc); acc = fmaf(x.y, y[k].y, acc);
+        acc = fmaf(x.z, y[k].z, acc); acc = fmaf(x.w, y[k].w, acc);
+      }
+    }
+    for (; e < d4; ++e) {
+      const float4 x = p4[e], y = __ldg(q4 + e);
+      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
+  }
+}
+
 // exact re-scoring of the ambiguous (user, item) pairs; blockIdx.y = the producing CTA's list segment
 __global__ void __launch_bounds__(256)
 tc_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
@@ -428,7 +516,18 @@ tc_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int 
       const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
       const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
       float acc = 0.f;
-      for (int e = 0; e < d / 4; ++e) {
+      int e = 0;
+      for (; e + 8 <= d / 4; e += 8) {   // a whole 128-byte line of each row in flight at once, consumed in k order
+        float4 x[8], y[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = __ldg(p4 + e + k); y[k] = __ldg(q4 + e + k); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc = fmaf(x[k].x, y[k].x, acc); acc = fmaf(x[k].y, y[k].y, acc);
+          acc = fmaf(x[k].z, y[k].z, acc); acc = fmaf(x[k].w, y[k].w, acc);
+        }
+      }
+      for (; e < d / 4; ++e) {
         const float4 x = __ldg(p4 + e), y = __ldg(q4 + e);
         acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
       }
@@ -502,10 +601,16 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
 
   APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 4 * 65536 + 16, st));
   { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
-  tc_prep_kernel<<<grid_for(int64_t(W.n_utiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
-      P, d, users, 0, n_users, L.nchunk, L.tile_bytes, 1, L.split2, gamma, a_img, uscale);
-  tc_prep_kernel<<<grid_for(int64_t(W.n_itiles) * 128 * L.nchunk * 8), 256, 0, st>>>(
-      Q, d, nullptr, item_lo, n_items, L.nchunk, L.tile_bytes, 0, L.split2, gamma, b_img, nullptr);
+  auto prep = [&](const float* T, const int32_t* ids, int lo, int n, int n_tiles, int is_a, unsigned char* img, float* us) {
+    const int64_t thr = int64_t(n_tiles) * 128 * (d / 8);
+    if (L.split2 && d == 64) tc_prep_split2_kernel<8><<<grid_for(thr), 256, 0, st>>>(T, ids, lo, n, L.tile_bytes, is_a, gamma, img, us);
+    else if (L.split2 && d == 128) tc_prep_split2_kernel<16><<<grid_for(thr), 256, 0, st>>>(T, ids, lo, n, L.tile_bytes, is_a, gamma, img, us);
+    else if (L.split2 && d == 256) tc_prep_split2_kernel<32><<<grid_for(thr), 256, 0, st>>>(T, ids, lo, n, L.tile_bytes, is_a, gamma, img, us);
+    else tc_prep_kernel<<<grid_for(int64_t(n_tiles) * 128 * L.nchunk * 8), 256, 0, st>>>(T, d, ids, lo, n, L.nchunk, L.tile_bytes, is_a,
+                                                                                      L.split2, gamma, img, us);
+  };
+  prep(P, users, 0, n_users, W.n_utiles, 1, a_img, uscale);
+  prep(Q, nullptr, item_lo, n_items, W.n_itiles, 0, b_img, nullptr);
   tc_norm_max_kernel<<<(W.n_itiles * 4 + 255) / 256, 256, 0, st>>>(b_img, W.n_itiles, L.nchunk, L.tile_bytes);
   APR_LAUNCH_CHECK();
 
@@ -556,8 +661,16 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
     APR_CUDA_CHECK(attr_err);
   }
   APR_LAUNCH_CHECK();
-  tc_rescore_kernel<<<dim3(std::max(1, std::min(64, cap_cta / 256 + 1)), n_ctas), 256, 0, st>>>(P, Q, d, users, spos, amb,
-                                                                                              amb_count, cap_cta, position);
+  const size_t rs_smem = size_t(TC_BM) * (d / 4 + 1) * sizeof(float4);
+  if (d % 4 == 0 && rs_smem <= 200 * 1024) {
+    APR_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
+    const int gx = std::max(1, std::min(8, (sms * 4) / std::max(1, n_ctas)));
+    tc_rescore_tile_kernel<<<dim3(gx, n_ctas), 512, rs_smem, st>>>(P, Q, d, users, n_users, W.n_utiles, spos, amb, amb_count,
+                                                                  cap_cta, position);
+  } else {
+    tc_rescore_kernel<<<dim3(std::max(1, std::min(64, cap_cta / 256 + 1)), n_ctas), 256, 0, st>>>(P, Q, d, users, spos, amb,
+                                                                                                amb_count, cap_cta, position);
+  }
   APR_LAUNCH_CHECK();
   return launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st);
 }
