@@ -95,6 +95,7 @@ _SIGNATURES = {
     "apr_eval_fullrank_tc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P,
                                             _P]),
     "apr_eval_tc_ambiguous": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
+    "apr_eval_tc_timing": (ctypes.c_int, [c_int32, POINTER(c_float)]),
     "apr_sum_squares": (ctypes.c_int, [_P, c_int64, _P, _P]),
 }
 

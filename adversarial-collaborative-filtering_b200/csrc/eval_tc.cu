@@ -565,7 +565,29 @@ int launch_excl_correction(const float* P, const float* Q, int d, const int32_t*
 
 using namespace apr;
 
+// optional phase timing (apr_eval_tc_timing): events around the GEMM kernel of the most recent apr_eval_fullrank_tc call
+static bool g_tc_timing = false;
+static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
+static bool g_tc_ev_valid = false;
+
 extern "C" {
+
+int apr_eval_tc_timing(int32_t enable, float* gemm_ms_out) {
+  if (gemm_ms_out) {
+    *gemm_ms_out = -1.f;
+    if (g_tc_ev_valid) {
+      APR_CUDA_CHECK(cudaEventSynchronize(g_tc_ev[1]));
+      APR_CUDA_CHECK(cudaEventElapsedTime(gemm_ms_out, g_tc_ev[0], g_tc_ev[1]));
+    }
+  }
+  if (enable && !g_tc_ev[0]) {
+    APR_CUDA_CHECK(cudaEventCreate(&g_tc_ev[0]));
+    APR_CUDA_CHECK(cudaEventCreate(&g_tc_ev[1]));
+  }
+  g_tc_timing = enable != 0;
+  if (!g_tc_timing) g_tc_ev_valid = false;
+  return APR_OK;
+}
 
 int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d) {
   if (n_users < 1 || n_items < 1 || !valid_dim(d) || (d % 8) != 0 || d > 256) return -1;
@@ -645,6 +667,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   if (cap_cta < 16) return APR_E_UNSUPPORTED;
   const int32_t meta[2] = {n_ctas, cap_cta};
   APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
+  if (g_tc_timing) APR_CUDA_CHECK(cudaEventRecord(g_tc_ev[0], st));
   {
     cudaError_t attr_err = cudaSuccess;
     auto launch = [&](auto kern) {
@@ -660,6 +683,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
     else launch(tc_count_kernel<0, 0>);
     APR_CUDA_CHECK(attr_err);
   }
+  if (g_tc_timing) { APR_CUDA_CHECK(cudaEventRecord(g_tc_ev[1], st)); g_tc_ev_valid = true; }
   APR_LAUNCH_CHECK();
   const size_t rs_smem = size_t(TC_BM) * (d / 4 + 1) * sizeof(float4);
   if (d % 4 == 0 && rs_smem <= 200 * 1024) {

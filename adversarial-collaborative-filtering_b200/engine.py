@@ -241,6 +241,13 @@ def tc_supported(d: int) -> bool:
     return d % 8 == 0 and d <= 256
 
 
+def eval_tc_timing(enable: bool) -> float:
+    """Switch the GEMM-kernel event timing of eval_fullrank_tc on/off; returns the last timed kernel's ms (-1: none)."""
+    ms = ctypes.c_float(-1.0)
+    _lib.check(_lib.lib().apr_eval_tc_timing(1 if enable else 0, ctypes.byref(ms)))
+    return float(ms.value)
+
+
 def eval_fullrank_tc(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, excl_idx,
                      position: Optional[torch.Tensor] = None, check: bool = True):
     """Positions through the tcgen05 bf16x3 filter + exact re-scoring (same results as eval_fullrank(exact=True)).

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--dim", type=int, default=CFG["d"])
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -446,6 +447,13 @@ def main_single(args):
             "data": "synthetic", "config": workload_config(args), "roofline": roofline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks}
 
+    # ---- SURVEY 8(d) variants on the same tables: batch sweep 2^9 .. 2^20 and the Zipf(1.05)-items contention case ---
+    if not args.no_variants and rank == 0:
+        try:
+            line["variants"] = bench_variants(torch, engine, sess, model, args, hp, rng, dev)
+        except Exception as e:
+            line["variants"] = {"error": repr(e)}
+
     # ---- second headline metric: full-rank evaluation users/s (BASELINE.json configs[2] shape) ------------
     if not args.no_eval and rank == 0:
         try:
@@ -465,6 +473,59 @@ def main_single(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def zipf_items(rng, shape, items, s=1.05):
+    """Bounded Zipf(s) over [0, items): p(k) ~ (k+1)^-s, by inverse CDF."""
+    cdf = np.cumsum(np.arange(1, items + 1, dtype=np.float64) ** (-s))
+    cdf /= cdf[-1]
+    return np.minimum(np.searchsorted(cdf, rng.random(shape)), items - 1).astype(np.int32)
+
+
+def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
+    """Short device-resident runs of the same step on the same tables (ids in HBM, CUDA events, >= 3 warm-up steps).
+    Not bench lines: they document the batch sweet spot and the duplicate-heavy regime named in SURVEY 8(d)."""
+    U, I, d = args.users, args.items, args.dim
+    P, Q, aP, aQ = model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q
+
+    def run(B, ids_fn, target_triples):
+        CH = max(1, min(256, (1 << 22) // B))
+        n_chunks = max(1, int(round(target_triples / (CH * B))))
+        ws = sess.workspace(CH, B, d)
+        chunks = [[torch.from_numpy(x).to(dev) for x in ids_fn(CH, B)] for _ in range(n_chunks + 1)]
+        engine.train_steps(P, Q, aP, aQ, *chunks[0], *hp, ws, mode=args.mode)   # warm-up: CH >= 4 steps
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for c in chunks[1:]:
+            engine.train_steps(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        steps = n_chunks * CH
+        cnt = ws.unique_counts(CH).astype(np.int64)          # unique rows of the last chunk's steps
+        out = {"batch": B, "steps": steps, "ms_per_step": ms / steps, "triples_per_s": steps * B / (ms * 1e-3),
+               "unique_rows_per_triple": float(cnt.sum()) / (CH * B)}
+        del ws, chunks
+        torch.cuda.empty_cache()
+        return out
+
+    uniform = lambda n, B: synth_triples(rng, n, B, U, I)
+    sweep = []
+    for lb in (9, 12, 14, 15, 16, 17, 18, 20):
+        B = 1 << lb
+        sweep.append(run(B, uniform, 32e6 if lb >= 14 else 4096 * B))
+    best = max(sweep, key=lambda r: r["triples_per_s"])
+
+    def zipf(n, B):
+        u = rng.integers(0, U, size=(n, B), dtype=np.int32)
+        i = zipf_items(rng, (n, B), I)
+        j = rng.integers(0, I, size=(n, B), dtype=np.int32)
+        return u, i, j
+
+    z = run(args.batch, zipf, 16e6)
+    z["items"] = "positives ~ Zipf(1.05) over %d items, negatives uniform" % I
+    return {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z}
 
 
 def bench_eval(torch, engine, dev, tc_peak):
@@ -503,12 +564,27 @@ def bench_eval(torch, engine, dev, tc_peak):
         ms, r = timed(lambda: engine.eval_fullrank_tc(*a, check=False)[0])
         pos_tc = r
         _, namb = engine.eval_fullrank_tc(*a)
-        issued = 2.0 * U * I * 3 * d / (ms * 1e-3) / 1e12
+        # the GEMM + counting kernel alone: CUDA events recorded by the library around that launch (its own stream)
+        engine.eval_tc_timing(True)
+        kms = []
+        for _ in range(max(2, reps)):
+            engine.eval_fullrank_tc(*a, check=False)
+            torch.cuda.synchronize()
+            kms.append(engine.eval_tc_timing(True))
+        engine.eval_tc_timing(False)
+        k_ms = float(np.mean(kms[1:]))
+        flops = 2.0 * U * I * 3 * d
+        issued_call = flops / (ms * 1e-3) / 1e12
+        issued_kernel = flops / (k_ms * 1e-3) / 1e12
         res["tensor_core"] = {"users_per_s": U / (ms * 1e-3), "ms": ms, "ambiguous_pairs_rescored": namb,
-                              "roofline": {"bound": "tensor", "achieved": issued, "peak": tc_peak, "unit": "TFLOP/s",
-                                           "frac": issued / tc_peak, "traffic": None,
-                                           "note": "issued bf16 flops = 3 x useful (hi*hi + hi*lo + lo*hi split); whole "
-                                                   "call incl. operand split, exact re-scoring and exclusion correction"}}
+                              "gemm_kernel_ms": k_ms,
+                              "roofline": {"bound": "tensor", "achieved": issued_kernel, "peak": tc_peak, "unit": "TFLOP/s",
+                                           "frac": issued_kernel / tc_peak, "traffic": None, "kernel": "tc_count_kernel",
+                                           "whole_call_achieved": issued_call, "whole_call_frac": issued_call / tc_peak,
+                                           "note": "issued bf16 flops = 3 x useful (hi*hi + hi*lo + lo*hi split); "
+                                                   "achieved/frac = the tcgen05 GEMM + counting kernel alone (CUDA events "
+                                                   "around its launch); whole_call_* also carries the operand split, the "
+                                                   "exact re-scoring and the exclusion correction"}}
         if exact_too:
             ms_e, pos_e = timed(lambda: engine.eval_fullrank(*a, 0, exact=True)[0])
             res["exact_fp32"] = {"users_per_s": U / (ms_e * 1e-3), "ms": ms_e, "fp32_tflops": 2.0 * U * I * d / (ms_e * 1e-3) / 1e12}

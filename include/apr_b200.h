@@ -172,6 +172,11 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
 int apr_eval_tc_ambiguous(const void* workspace, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
                           apr_stream_t stream);
 
+/* Measurement hook (bench.py): enable != 0 makes every following apr_eval_fullrank_tc record CUDA events around its GEMM +
+ * counting kernel on the caller's stream; *gemm_ms_out (may be NULL) receives the duration of the most recent timed call
+ * (-1 if none).  Not thread-safe; leave disabled in production. */
+int apr_eval_tc_timing(int32_t enable, float* gemm_ms_out);
+
 /* ---- K11: np.linalg.norm(embedding_P) of utils.py:92-97: *out (device double) = sum of squares. */
 int apr_sum_squares(const float* x, int64_t n, double* out, apr_stream_t stream);
 
