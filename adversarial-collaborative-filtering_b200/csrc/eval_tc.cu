@@ -5,17 +5,21 @@
 //   1. prep   P-tile and Q are split into bf16 hi + lo parts and written as ready-made shared-memory IMAGES: per 128-row
 //             tile, per 64-element K chunk, a 16 KB block already in the SWIZZLE_128B K-major layout tcgen05 expects.
 //             K is the concatenation  A' = [a_hi | a_hi | a_lo],  B' = [b_hi | b_lo | b_hi]  (K' = 3d), so ONE bf16 GEMM
-//             accumulates a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32:  |s_tc - s_fp32chain| <= gamma ||p|| ||q||.
-//   2. GEMM   one CTA = 128 users x a range of item tiles.  Warp 0: producer, one elected lane streams the 16 KB chunk
-//             images with cp.async.bulk (TMA engine, mbarrier complete_tx).  Warp 1: allocates TMEM, one elected lane
-//             issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) into a double-buffered fp32 accumulator
-//             (2 x 128 TMEM columns), tcgen05.commit frees smem stages / publishes accumulators.  Warps 2-5: epilogue,
-//             tcgen05.ld 32 columns at a time, each thread owns one user row:
-//                   s - s_pos >  eps  -> counted            s - s_pos < -eps -> not counted
-//                   otherwise         -> (user, item) appended to the ambiguous list      eps = gamma ||p_u|| ||q_c||
+//             accumulates a_hi b_hi + a_hi b_lo + a_lo b_hi in fp32:  |s_tc - s_fp32chain| <= gamma ||p|| ||q||
+//             (gamma = 3.03 * 2^-18 + 3.54 d * 2^-23, derived where it is set in apr_eval_fullrank_tc).
+//   2. GEMM   one CTA = 128 users x a range of item tiles, 18 warps.  Warp 16: producer, one lane streams the 16 KB
+//             chunk images with cp.async.bulk (TMA engine, mbarrier complete_tx).  Warp 17: allocates TMEM; the lane
+//             elect.sync picks issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) into a double-buffered
+//             fp32 accumulator (2 x 128 TMEM columns); tcgen05.commit frees smem stages / publishes accumulators.  Its
+//             issue loop is the kernel's critical chain, hence the compile-time chunk layout (template NCHUNK/CPS).
+//             Warps 0-15: epilogue, tcgen05.ld of one 32-column block each; a thread owns one user row.  With
+//             w = s - s_pos and E = gamma ||p_u|| max_block ||q_c||:
+//                   w >  E  -> counted (sign bit of E - w)      w < -E -> not counted
+//                   |w| <= E -> (user, item) appended to this CTA's segment of the ambiguous list
 //             The score matrix never leaves TMEM/registers.
-//   3. exact  the ambiguous pairs are re-scored with the fp32 fma chain (eval.cu order) and counted; train items and the
-//             held-out item are removed by the sparse correction kernel of eval.cu.
+//   3. exact  the ambiguous pairs are re-scored with the fp32 fma chain (eval.cu order) and counted -- per list segment,
+//             with that segment's 128 user rows staged in shared memory; train items and the held-out item are
+//             removed by the sparse correction kernel of eval.cu.
 // Every mbarrier wait is bounded (error flag instead of a hang).
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -615,9 +619,13 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   int2* amb = reinterpret_cast<int2*>(base + W.off_amb);
   int* amb_count = reinterpret_cast<int*>(base + W.off_cnt);
   const int amb_cap = int(tc_amb_cap(n_users, n_items));
-  // |s_tc - s_chain| <= gamma ||p|| ||q||:  3*2^-16 (dropped lo*lo and split residuals) + (3d + d) 2^-23 (fp32 accumulation
-  // of the tensor core, worst case, plus the rounding of the fma chain itself)
-  const float gamma = 3.0f / 65536.0f + float(4 * d) / 8388608.0f;
+  // |s_tc - s_chain| <= gamma ||p|| ||q||, every term a worst case (Cauchy-Schwarz: sum |a_k b_k| <= ||p|| ||q||):
+  //   split     a = hi + lo + r with |r| <= 2^-18 |a| (two round-to-nearest bf16 steps, x - hi is exact in fp32); the
+  //             GEMM keeps hi*hi + hi*lo + lo*hi and drops lo*lo + r_a b + a r_b            <= 3 * 2^-18 * 1.01
+  //   tensor    3d exact bf16 x bf16 products summed into an fp32 accumulator in an unknown order, each addition
+  //             charged a full truncation ulp of the running magnitude                        <= 3d * 2^-23 * 1.01
+  //   chain     the fp32 fma chain it is compared with (oracle score order)                   <= d * 2^-24 * 1.02
+  const float gamma = 3.03f / 262144.0f + float(d) * 3.54f / 8388608.0f;
   const int sms = sm_count();
   auto grid_for = [&](int64_t n) { return int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(sms) * 16))); };
 
