@@ -461,82 +461,57 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
   }
 }
 
-// exact re-scoring, shared-memory variant: every pair of a list segment belongs to ONE user tile (the producing CTA's),
-// so the block stages those 128 rows of P once (row stride d + 4 floats: quarter-warp LDS.128 of distinct rows spread
-// over the banks) and only the item rows travel per pair.  Halves the L2 traffic the plain variant is bound by.
+// exact re-scoring of the ambiguous pairs, one list segment per blockIdx.y.
+// Eight lanes share a pair: lane s holds the s-th 16-byte piece of the current 128-byte line of both rows, so a warp's
+// load instruction covers four whole lines (4 L1 wavefronts instead of the 32 of a lane-per-pair gather -- the L1 data
+// pipe is what bounds this step; the segment's 128 user rows stay L1-resident).  The fma chain stays the oracle's: the
+// accumulator walks the eight lanes in k order, each step taken from the lane that owns those four elements (every lane
+// computes, the shuffle picks the owner's value).
 __global__ void __launch_bounds__(512)
-tc_rescore_tile_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
-                       int n_users, int n_utiles, const float* __restrict__ spos, const int2* __restrict__ amb,
-                       const int* __restrict__ amb_count, int amb_cap, int32_t* __restrict__ position) {
-  extern __shared__ float4 sP4[];
+tc_rescore_group_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
+                        const float* __restrict__ spos, const int2* __restrict__ amb, const int* __restrict__ amb_count,
+                        int amb_cap, int32_t* __restrict__ position) {
   const int seg = blockIdx.y;
   const int n = min(amb_count[seg], amb_cap);
-  if (int(blockIdx.x * blockDim.x) >= n) return;
-  const int m0 = (seg % n_utiles) * TC_BM;
-  const int d4 = d >> 2, stride4 = d4 + 1;
-  for (int idx = threadIdx.x; idx < TC_BM * d4; idx += blockDim.x) {
-    const int r = idx / d4, c = idx - r * d4;
-    const int uidx = m0 + r;
-    sP4[r * stride4 + c] = uidx < n_users ? __ldg(reinterpret_cast<const float4*>(P + int64_t(users[uidx]) * d) + c)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
+  if (int(blockIdx.x * (blockDim.x >> 3)) >= n) return;
+  const int d4 = d >> 2;
   const int2* list = amb + int64_t(seg) * amb_cap;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const int2 a = list[t];
-    const float4* p4 = sP4 + (a.x - m0) * stride4;
+  const int lane = threadIdx.x & 31, s8 = lane & 7, gbase = lane & ~7;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = (gridDim.x * blockDim.x) >> 3;
+  const int nlines = (d4 + 7) >> 3;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // whole warps iterate together (the shuffles need every lane): the trip count comes from the warp's first group
+  for (int t0 = group - (lane >> 3); t0 < n; t0 += ngroups) {
+    const int t = t0 + (lane >> 3);
+    const bool valid = t < n;
+    const int2 a = list[valid ? t : t0];
+    const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
     const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
     float acc = 0.f;
-    int e = 0;
-    for (; e + 8 <= d4; e += 8) {   // a whole 128-byte line of the item row in flight at once, consumed in k order
-      float4 y[8];
+    for (int l0 = 0; l0 < nlines; l0 += 4) {   // up to four lines of each row in flight
+      float4 x[4], y[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) y[k] = __ldg(q4 + e + k);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 x = p4[e + k];
-        acc = fmaf(x.x, y[k].x, acc); acc = fmaf(x.y, y[k].y, acc);
-        acc = fmaf(x.z, y[k].z, acc); acc = fmaf(x.w, y[k].w, acc);
+      for (int l = 0; l < 4; ++l) {
+        const int e = (l0 + l) * 8 + s8;
+        const bool in = (l0 + l) < nlines && e < d4;   // past the row: 0 * 0 leaves the accumulator unchanged
+        y[l] = in ? __ldg(q4 + e) : zero4;
+        x[l] = in ? __ldg(p4 + e) : zero4;
       }
-    }
-    for (; e < d4; ++e) {
-      const float4 x = p4[e], y = __ldg(q4 + e);
-      acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-    }
-    if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
-  }
-}
-
-// exact re-scoring of the ambiguous (user, item) pairs; blockIdx.y = the producing CTA's list segment
-__global__ void __launch_bounds__(256)
-tc_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
-                  const float* __restrict__ spos, const int2* __restrict__ amb, const int* __restrict__ amb_count,
-                  int amb_cap, int32_t* __restrict__ position) {
-  for (int seg = blockIdx.y; seg < int(gridDim.y); seg += gridDim.y) {
-    const int n = min(amb_count[seg], amb_cap);
-    const int2* list = amb + int64_t(seg) * amb_cap;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-      const int2 a = list[t];
-      const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
-      const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
-      float acc = 0.f;
-      int e = 0;
-      for (; e + 8 <= d / 4; e += 8) {   // a whole 128-byte line of each row in flight at once, consumed in k order
-        float4 x[8], y[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { x[k] = __ldg(p4 + e + k); y[k] = __ldg(q4 + e + k); }
+      for (int l = 0; l < 4; ++l) {
+        if (l0 + l < nlines) {                   // warp-uniform
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          acc = fmaf(x[k].x, y[k].x, acc); acc = fmaf(x[k].y, y[k].y, acc);
-          acc = fmaf(x[k].z, y[k].z, acc); acc = fmaf(x[k].w, y[k].w, acc);
+          for (int st = 0; st < 8; ++st) {
+            float v = fmaf(x[l].x, y[l].x, acc);
+            v = fmaf(x[l].y, y[l].y, v);
+            v = fmaf(x[l].z, y[l].z, v);
+            v = fmaf(x[l].w, y[l].w, v);
+            acc = __shfl_sync(0xffffffffu, v, gbase | st);
+          }
         }
       }
-      for (; e < d / 4; ++e) {
-        const float4 x = __ldg(p4 + e), y = __ldg(q4 + e);
-        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-      }
-      if (acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
     }
+    if (valid && s8 == 0 && acc >= spos[a.x]) atomicAdd(&position[a.x], 1);
   }
 }
 
@@ -693,15 +668,9 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   }
   if (g_tc_timing) { APR_CUDA_CHECK(cudaEventRecord(g_tc_ev[1], st)); g_tc_ev_valid = true; }
   APR_LAUNCH_CHECK();
-  const size_t rs_smem = size_t(TC_BM) * (d / 4 + 1) * sizeof(float4);
-  if (d % 4 == 0 && rs_smem <= 200 * 1024) {
-    APR_CUDA_CHECK(cudaFuncSetAttribute(tc_rescore_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
-    const int gx = std::max(1, std::min(8, (sms * 4) / std::max(1, n_ctas)));
-    tc_rescore_tile_kernel<<<dim3(gx, n_ctas), 512, rs_smem, st>>>(P, Q, d, users, n_users, W.n_utiles, spos, amb, amb_count,
-                                                                  cap_cta, position);
-  } else {
-    tc_rescore_kernel<<<dim3(std::max(1, std::min(64, cap_cta / 256 + 1)), n_ctas), 256, 0, st>>>(P, Q, d, users, spos, amb,
-                                                                                                amb_count, cap_cta, position);
+  {  // d % 8 == 0 here (checked on entry), so rows are whole float4 pieces
+    const int gx = std::max(1, std::min(8, (sms * 6) / std::max(1, n_ctas)));
+    tc_rescore_group_kernel<<<dim3(gx, n_ctas), 512, 0, st>>>(P, Q, d, users, spos, amb, amb_count, cap_cta, position);
   }
   APR_LAUNCH_CHECK();
   return launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st);
