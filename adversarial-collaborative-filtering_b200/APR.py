@@ -36,6 +36,7 @@ class Session(object):
         self.device = engine.require_cuda()
         self.mode = int(os.environ.get("APR_B200_STEP_MODE", "0")) if mode is None else mode
         self._ws = None
+        self._host_pipe = None
 
     def __enter__(self):
         return self
@@ -50,6 +51,11 @@ class Session(object):
         return self._ws
 
     def train_steps(self, model, U, I, J, adver: bool, stats=None) -> None:
+        """S steps over the batches U/I/J [S, B].  Device tensors run as they are; HOST batches (CPU tensors or ndarrays,
+        pinned or not -- the reference's feed_dict, utils.py:117-119) are streamed: chunk k+1 travels host->device on a
+        copy stream while chunk k trains, so the copies hide behind the step kernels."""
+        if not (isinstance(U, torch.Tensor) and U.is_cuda):
+            return self._train_steps_host(model, U, I, J, adver, stats)
         S, B = U.shape
         chunk = max(1, min(S, MAX_CHUNK_TRIPLES // max(B, 1)))
         ws = self.workspace(chunk, B, model.embedding_size)
@@ -58,6 +64,47 @@ class Session(object):
             engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, U[s0:s1], I[s0:s1], J[s0:s1],
                                model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws, mode=self.mode,
                                stats=None if stats is None else stats[s0:s1])
+
+    def _train_steps_host(self, model, U, I, J, adver: bool, stats=None) -> None:
+        host = []
+        for x in (U, I, J):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+            t = t.reshape(t.shape[0], -1)
+            host.append(t if t.dtype == torch.int32 else t.to(torch.int32))
+        S, B = host[0].shape
+        chunk = max(1, min(S, MAX_CHUNK_TRIPLES // max(B, 1)))
+        ws = self.workspace(chunk, B, model.embedding_size)
+        st = self._host_pipe
+        if st is None or st["dev"][0].shape != (3, chunk, B):
+            st = {"dev": [torch.empty((3, chunk, B), dtype=torch.int32, device=self.device) for _ in range(2)],
+                  "pin": [None, None], "copy": torch.cuda.Stream(device=self.device),
+                  "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)]}
+            self._host_pipe = st
+        cur = torch.cuda.current_stream(self.device)
+        pinned = all(t.is_pinned() and t.is_contiguous() for t in host)
+        for k, s0 in enumerate(range(0, S, chunk)):
+            s1 = min(S, s0 + chunk)
+            n, b = s1 - s0, k & 1
+            dev = st["dev"][b]
+            if k >= 2:
+                st["copy"].wait_event(st["free"][b])     # the steps that read this buffer two chunks ago are done
+            if not pinned:                                 # pageable input: stage through a pinned buffer of our own
+                if st["pin"][b] is None or st["pin"][b].shape != (3, chunk, B):
+                    st["pin"][b] = torch.empty((3, chunk, B), dtype=torch.int32).pin_memory()
+                elif k >= 2:
+                    st["ready"][b].synchronize()           # its previous host->device copy has left the staging buffer
+                for q in range(3):
+                    st["pin"][b][q, :n].copy_(host[q][s0:s1])
+            with torch.cuda.stream(st["copy"]):
+                for q in range(3):
+                    src = host[q][s0:s1] if pinned else st["pin"][b][q, :n]
+                    dev[q, :n].copy_(src, non_blocking=True)
+                st["ready"][b].record(st["copy"])
+            cur.wait_event(st["ready"][b])
+            engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, dev[0, :n], dev[1, :n],
+                               dev[2, :n], model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws,
+                               mode=self.mode, stats=None if stats is None else stats[s0:s1])
+            st["free"][b].record(cur)
 
 
 class MF:

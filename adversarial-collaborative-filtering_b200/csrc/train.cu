@@ -980,7 +980,8 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
   int32_t* tkey_i = at<int32_t>(ws, L.off_tkey_i);
   int32_t* tval_i = at<int32_t>(ws, L.off_tval_i);
   const int threads = 256;
-  const int64_t cap = int64_t(sm_count()) * 16;
+  static const int prep_bps = env_int("APR_PREP_BLOCKS", 16);
+  const int64_t cap = int64_t(sm_count()) * std::max(1, prep_bps);
   // table keys = -1, table values = 0
   APR_CUDA_CHECK(cudaMemsetAsync(tkey_u, 0xFF, size_t(int64_t(ns) * L.Tu * 4), st));
   APR_CUDA_CHECK(cudaMemsetAsync(tval_u, 0, size_t(int64_t(ns) * L.Tu * 4), st));

@@ -190,3 +190,40 @@ def test_video_real_data_epoch_matches_oracle(cuda_device):
             p, _, _, _ = O.eval_fullrank_user(gP, gQ, uu_, int(z["test_i"][uu_]),
                                               ods.trainList[uu_] if uu_ < len(ods.trainList) else [], ds.num_items, 1)
             assert p == pos[uu_]
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_batches_stream_like_device_batches(pinned, monkeypatch):
+    """Session.train_steps with HOST batches (chunked H2D on a copy stream, double-buffered) must leave the tables the
+    device-resident path leaves -- same kernels, same step order -- over several chunks incl. a ragged last one.
+    (BPR steps: shared-item sums use float REDs whose order may differ between runs, and APR amplifies last-bit
+    differences chaotically; a wrong or stale chunk would show as a gross difference either way.)"""
+    import torch
+    import types
+    from apr_b200 import APR
+    U, I, d, B, S = 3000, 2000, 64, 512, 23
+    monkeypatch.setattr(APR, "MAX_CHUNK_TRIPLES", 4 * B)          # 4 steps per chunk -> 6 chunks, the last one of 3
+    rng = np.random.RandomState(5)
+    ids = [rng.randint(0, n, (S, B)).astype(np.int32) for n in (U, I, I)]
+    args = types.SimpleNamespace(embed_size=d, lr=0.05, reg=0.0, dns=1, adv="grad", eps=0.5, adver=1, reg_adv=1.0, epochs=0,
+                                 seed=2019)
+    out = []
+    for host in (False, True):
+        model = APR.MF(U, I, args)
+        model.build_graph()
+        sess = APR.Session()
+        stats = torch.zeros((S, 2), dtype=torch.float32, device=model.device)
+        if host:
+            xs = [torch.from_numpy(x) for x in ids]
+            if pinned:
+                xs = [x.pin_memory() for x in xs]
+            for _ in range(2):                                      # second pass re-uses the staging buffers
+                sess.train_steps(model, *xs, adver=False, stats=stats)
+        else:
+            xs = [torch.from_numpy(x).to(model.device) for x in ids]
+            for _ in range(2):
+                sess.train_steps(model, *xs, adver=False, stats=stats)
+        torch.cuda.synchronize()
+        out.append((model.embedding_P.clone(), model.embedding_Q.clone(), stats.clone()))
+    for a, b in zip(out[0], out[1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
