@@ -382,6 +382,8 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
     const bool uvalid = uidx < n_users;
     const float sp = uvalid ? spos[uidx] : CUDART_INF_F;
     const float gu = uvalid ? user_scale[uidx] : 0.f;
+    // a non-finite held-out score (NaN / Inf in the user row or the held-out item row) makes every pair undecidable here
+    const float gue = (uvalid && !(fabsf(sp) < CUDART_INF_F)) ? CUDART_INF_F : gu;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
     int2* my_amb = amb + int64_t(cta) * amb_cap;           // amb_cap = capacity of ONE CTA's segment
     int cnt = 0;
@@ -409,10 +411,11 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         // select/add all issue on the ALU pipe (one warp instruction per 2 cycles per scheduler).  So the count is taken
         // on the FMA pipe instead -- sign bit of (E - w), summed with mad.hi -- and the band test is ONE min per score;
         // only a group of 8 columns that has a score inside the band is looked at element by element.
-        float E = fmaf(gu * qn[128 + (col0 >> 5)], 1.0f + 0x1p-21f, 1e-30f);
-        if (!(E < CUDART_INF_F)) E = CUDART_INF_F;        // non-finite norms: everything undecidable -> exact re-score
+        const float qmax = qn[128 + (col0 >> 5)];
+        float E = fmaf(gue * qmax, 1.0f + 0x1p-21f, 1e-30f);
+        if (!(E < 1e30f)) E = CUDART_INF_F;               // non-finite / near-overflow magnitudes: no sign-bit arithmetic
         const int ncols = item_hi - (n0 + col0);           // columns past item_hi (padding of the last tile) never count
-        if (ncols >= 32) {
+        if (ncols >= 32 && qmax < CUDART_INF_F && E < CUDART_INF_F) {   // uniform except for degenerate users
           unsigned c = 0u;
           float mg[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
 #pragma unroll
@@ -434,13 +437,17 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
               }
             }
           }
-        } else if (ncols > 0 && uvalid) {                   // ragged last block of the item range
+        } else if (ncols > 0 && uvalid) {
+          // ragged last block of the item range, a block holding an item row with a non-finite norm (its poisoned
+          // maximum would send all 32 columns of every user to the re-score), or a degenerate user: per-column bounds
 #pragma unroll
           for (int jx = 0; jx < 32; ++jx) {
             if (jx >= ncols) continue;
+            const float Ej = fmaf(gue * qn[col0 + jx], 1.0f + 0x1p-21f, 1e-30f);
             const float w = v[jx] - sp;
-            if (w > E) ++cnt;
-            else if (fabsf(w) <= E) {
+            const bool undecidable = !(Ej < 1e30f);      // NaN / Inf / near-overflow: the exact chain decides, whatever w is
+            if (!undecidable && w > Ej) ++cnt;
+            else if (undecidable || fabsf(w) <= Ej) {
               const int slot = atomicAdd(&s_amb_count, 1);
               if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
             }
