@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--eval-users", type=int, default=1 << 20,
+                    help="users of the tiled configs[4] evaluation run (multiple of 16384; 0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -50,6 +52,15 @@ def peaks():
         j = json.load(open(p))
         return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1590.0)), "measured"
     return 6650.0, 1590.0, "fallback"
+
+
+def sustained_tc_peak(burst):
+    """The sustained bf16 figure of MEASURED_PEAKS.json (cuBLAS back to back for seconds): the denominator for a kernel
+    timed inside a long run; the burst figure is for a kernel timed alone."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops_sustained", burst))
+    return burst
 
 
 class ClockSampler:
@@ -456,7 +467,7 @@ def main_single(args):
     # ---- second headline metric: full-rank evaluation users/s (BASELINE.json configs[2] shape) ------------
     if not args.no_eval and rank == 0:
         try:
-            line["eval"] = bench_eval(torch, engine, dev, tc_peak)
+            line["eval"] = bench_eval(torch, engine, dev, tc_peak, args.eval_users)
         except Exception as e:  # never lose the training line
             line["eval"] = {"error": repr(e)}
 
@@ -527,7 +538,7 @@ def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
     return {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z}
 
 
-def bench_eval(torch, engine, dev, tc_peak):
+def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
     """Full-rank leave-one-out evaluation (second headline metric): users/s with positions for HR@10/NDCG@10.
     Shapes: BASELINE.json configs[2] (yelp-sort shape, d=128) and a tile of configs[4] (10M items, d=256)."""
     out = {}
@@ -595,6 +606,58 @@ def bench_eval(torch, engine, dev, tc_peak):
 
     one(25677, 25815, 128, "yelp_shape_d128", True, 3)
     one(4096, 10_000_000, 256, "config5_tile_4096_users_x_10M_items_d256", False, 1)
+
+    def tiled(U_total, tile, I, d, tag):
+        """configs[4] as SURVEY 8(d) asks for it: >= 2^20 users against all 10 M items, in user tiles of one library call
+        each (the ambiguous-pair list of a call is sized by users x items/256, so a call takes a tile of the users)."""
+        g = torch.Generator(device=dev)
+        g.manual_seed(2019)
+        P = torch.randn((U_total, d), device=dev, generator=g) / d ** 0.5
+        Q = torch.randn((I + 1, d), device=dev, generator=g) / d ** 0.5
+        test = torch.randint(0, I, (U_total,), device=dev, dtype=torch.int32, generator=g)
+        users = torch.arange(U_total, device=dev, dtype=torch.int32)
+        ptr = torch.arange(0, tile + 1, device=dev, dtype=torch.int64)     # exclusion = the held-out item
+        pos = torch.zeros(U_total, dtype=torch.int32, device=dev)
+
+        def call(k, check):
+            sl = slice(k * tile, (k + 1) * tile)
+            return engine.eval_fullrank_tc(P, Q, users[sl], test[sl], 0, I, ptr, test[sl], position=pos[sl], check=check)
+
+        _, namb = call(0, True)                                             # warm-up + capacity / error-flag check
+        pos[:tile].zero_()
+        torch.cuda.synchronize()
+        engine.eval_tc_timing(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = 0.0
+        e0.record()
+        for k in range(U_total // tile):
+            call(k, False)
+            kms += engine.eval_tc_timing(True) if k % 8 == 7 else 0.0     # sample the GEMM-kernel time of every 8th tile
+        e1.record()
+        torch.cuda.synchronize()
+        engine.eval_tc_timing(False)
+        ms = e0.elapsed_time(e1)
+        n_sampled = (U_total // tile) // 8
+        k_ms = kms / max(1, n_sampled)
+        flops_tile = 2.0 * tile * I * 3 * d
+        sus_peak = sustained_tc_peak(tc_peak)
+        out[tag] = {"users": U_total, "items": I, "d": d, "user_tile": tile, "ms": ms,
+                    "users_per_s": U_total / (ms * 1e-3), "ambiguous_pairs_first_tile": namb,
+                    "hr10": float((pos < 10).float().mean().item()), "gemm_kernel_ms_per_tile": k_ms,
+                    "roofline": {"bound": "tensor", "achieved": flops_tile / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
+                                 "peak": sus_peak, "peak_kind": "sustained (17 s run); burst peak %.1f" % tc_peak,
+                                 "unit": "TFLOP/s",
+                                 "frac": flops_tile / (k_ms * 1e-3) / 1e12 / sus_peak if k_ms > 0 else None,
+                                 "frac_of_burst_peak": flops_tile / (k_ms * 1e-3) / 1e12 / tc_peak if k_ms > 0 else None,
+                                 "whole_run_achieved": 2.0 * U_total * I * 3 * d / (ms * 1e-3) / 1e12,
+                                 "kernel": "tc_count_kernel<8,4>", "traffic": None,
+                                 "note": "issued bf16 flops = 3 x useful; frac = GEMM kernel of sampled tiles (library "
+                                         "CUDA events); whole_run_* = all tiles incl. operand split and exact re-scoring"}}
+        del P, Q
+        torch.cuda.empty_cache()
+
+    if eval_users > 0:
+        tiled(eval_users, 16384, 10_000_000, 256, "config5_%d_users_x_10M_items_d256" % eval_users)
     out["reference_logs"] = "yelp-sort full-rank eval 250-285 users/s (TF1 CPU, BASELINE.md 1.2)"
     return out
 
