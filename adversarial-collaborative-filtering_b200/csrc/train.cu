@@ -1196,7 +1196,7 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr); c.rec = at<int4>(ws, L.off_rec); c.iu_item = at<int32_t>(ws, L.off_iu_item);
   c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf);
   c.stats = stats;
-  c.flags = 0;
+  c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = step; c.s_end = step + 1; c.only_stage = stage;
   return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream));
 }
@@ -1253,20 +1253,30 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
   if (timing) for (auto& e : ev) cudaEventCreate(&e);
   for (int s = first_step; s < first_step + count; ++s) {
     int rc;
-    APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
-    APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
-    if (timing) cudaEventRecord(ev[6], ax.stream);
-    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
-                                 ws_bytes, stats, s, 3, ax.stream);
-    if (rc) return rc;
-    APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
-    if (timing) { cudaEventRecord(ev[7], ax.stream); cudaEventRecord(ev[0], st); }
+    // where the fast kernel (second stream) starts relative to the general stages: 0 = with stage 0, 1 = after stage 0
+    // and its barrier (the general path's dependent peer loads then do not queue behind the fast kernel's NVLink
+    // traffic during stage 0), 2 = after the whole general path (no overlap)
+    static const int order = env_int("APR_SHARD_ORDER", 0);
+    auto launch_fast = [&]() -> int {
+      APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
+      APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
+      if (timing) cudaEventRecord(ev[6], ax.stream);
+      const int r2 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
+                                             adver, ws, ws_bytes, stats, s, 3, ax.stream);
+      if (r2) return r2;
+      APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+      if (timing) cudaEventRecord(ev[7], ax.stream);
+      return APR_OK;
+    };
+    if (order == 0 || !adver) { if ((rc = launch_fast())) return rc; }
+    if (timing) cudaEventRecord(ev[0], st);
     if (adver) {
       rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
                                    ws_bytes, stats, s, 0, st);
       if (rc) return rc;
       if (timing) cudaEventRecord(ev[1], st);
       if ((rc = barrier())) return rc;
+      if (order == 1) { if ((rc = launch_fast())) return rc; }
     }
     if (timing) cudaEventRecord(ev[2], st);
     rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
@@ -1279,6 +1289,7 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
                                  ws_bytes, stats, s, 2, st);
     if (rc) return rc;
     if (timing) cudaEventRecord(ev[5], st);
+    if (order == 2 && adver) { if ((rc = launch_fast())) return rc; }
     APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
     if ((rc = barrier())) return rc;
     if (timing && adver) {
