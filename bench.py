@@ -499,6 +499,7 @@ def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
     P, Q, aP, aQ = model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q
 
     def run(B, ids_fn, target_triples):
+        nonlocal hp
         CH = max(1, min(256, (1 << 22) // B))
         n_chunks = max(1, int(round(target_triples / (CH * B))))
         ws = sess.workspace(CH, B, d)
@@ -535,7 +536,13 @@ def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
 
     z = run(args.batch, zipf, 16e6)
     z["items"] = "positives ~ Zipf(1.05) over %d items, negatives uniform" % I
-    return {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z}
+    # the reference's first phase (MF-BPR pretraining, APR.py:232-236): same step without the adversarial pass
+    hp_apr = hp
+    hp = hp_apr[:4] + (0,)
+    bpr = run(args.batch, uniform, 32e6)
+    bpr["note"] = "adver = 0: one forward/backward, Adagrad; same algorithmic bytes per triple as the APR step"
+    hp = hp_apr
+    return {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z, "bpr_step": bpr}
 
 
 def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
@@ -658,6 +665,35 @@ def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
 
     if eval_users > 0:
         tiled(eval_users, 16384, 10_000_000, 256, "config5_%d_users_x_10M_items_d256" % eval_users)
+
+    def sampled(U, I, d, C, tag):
+        """configs[1] (pinterest shape): He protocol, 99 sampled negatives + the held-out item per user
+        (utils.py:244-254).  Algorithmic bytes 4 d (1 + C) per user; the 2.5 MB item table is L2-resident,
+        so the figure is a gather rate, not an HBM roofline claim."""
+        g = torch.Generator(device=dev)
+        g.manual_seed(2019)
+        P = torch.randn((U, d), device=dev, generator=g) / d ** 0.5
+        Q = torch.randn((I, d), device=dev, generator=g) / d ** 0.5
+        cand = torch.randint(0, I, (U * C,), device=dev, dtype=torch.int32, generator=g)
+        ptr = torch.arange(0, (U + 1) * C, C, device=dev, dtype=torch.int64)
+        users = torch.arange(U, device=dev, dtype=torch.int32)
+        for _ in range(3):
+            pos, _ = engine.eval_candidates(P, Q, users, ptr, cand)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            pos, _ = engine.eval_candidates(P, Q, users, ptr, cand)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[tag] = {"users": U, "items": I, "d": d, "candidates_per_user": C, "ms": ms, "users_per_s": U / (ms * 1e-3),
+                    "gather_gb_per_s": 4.0 * d * (1 + C) * U / (ms * 1e-3) / 1e9,
+                    "hr10": float((pos < 10).float().mean().item()),
+                    "note": "item table (2.5 MB) is L2-resident: launch/L2 bound, no HBM roofline claimed"}
+
+    sampled(55187, 9916, 64, 100, "config2_pinterest_shape_sampled_d64")
     out["reference_logs"] = "yelp-sort full-rank eval 250-285 users/s (TF1 CPU, BASELINE.md 1.2)"
     return out
 
