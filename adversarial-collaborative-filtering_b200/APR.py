@@ -34,7 +34,11 @@ class Session(object):
 
     def __init__(self, mode: Optional[int] = None):
         self.device = engine.require_cuda()
-        self.mode = int(os.environ.get("APR_B200_STEP_MODE", "0")) if mode is None else mode
+        # -1 = automatic: the one-cluster persistent kernel (mode 2) for small batches whose steps are a few microseconds
+        # long (the reference's default B = 512: 14 us/step against 23 with per-phase launches), per-phase launches
+        # with the fast kernel on a second stream (mode 0) otherwise
+        self.mode = int(os.environ.get("APR_B200_STEP_MODE", "-1")) if mode is None else mode
+        self.cluster_max_batch = int(os.environ.get("APR_B200_CLUSTER_MAX_BATCH", "768"))
         self._ws = None
         self._host_pipe = None
 
@@ -50,6 +54,11 @@ class Session(object):
             self._ws = engine.TrainWorkspace(n_steps, batch, d, self.device)
         return self._ws
 
+    def step_mode(self, batch: int) -> int:
+        if self.mode >= 0:
+            return self.mode
+        return 2 if batch <= self.cluster_max_batch else 0
+
     def train_steps(self, model, U, I, J, adver: bool, stats=None) -> None:
         """S steps over the batches U/I/J [S, B].  Device tensors run as they are; HOST batches (CPU tensors or ndarrays,
         pinned or not -- the reference's feed_dict, utils.py:117-119) are streamed: chunk k+1 travels host->device on a
@@ -62,8 +71,8 @@ class Session(object):
         for s0 in range(0, S, chunk):
             s1 = min(S, s0 + chunk)
             engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, U[s0:s1], I[s0:s1], J[s0:s1],
-                               model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws, mode=self.mode,
-                               stats=None if stats is None else stats[s0:s1])
+                               model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws,
+                               mode=self.step_mode(B), stats=None if stats is None else stats[s0:s1])
 
     def _train_steps_host(self, model, U, I, J, adver: bool, stats=None) -> None:
         host = []
@@ -103,7 +112,7 @@ class Session(object):
             cur.wait_event(st["ready"][b])
             engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, dev[0, :n], dev[1, :n],
                                dev[2, :n], model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws,
-                               mode=self.mode, stats=None if stats is None else stats[s0:s1])
+                               mode=self.step_mode(B), stats=None if stats is None else stats[s0:s1])
             st["free"][b].record(cur)
 
 

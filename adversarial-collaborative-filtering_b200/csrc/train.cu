@@ -280,6 +280,7 @@ struct StepCtx {
   int flags;     // tuning switches (APR_STEP_FLAGS)
   int s_begin, s_end;  // steps of this launch
   int only_stage;      // -1: whole step; 0,1,2: that general stage; 3: fast kernel (sharded driver, one launch per call)
+  int cluster_sync;    // persistent kernel launched as ONE thread-block cluster: phase barriers are cluster barriers
 };
 
 __device__ __forceinline__ float* shard_row(float* const* base, int id, int d, const StepCtx& c) {
@@ -799,6 +800,9 @@ __global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fas
 template <int G, int V, bool FULL>
 __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
   cg::grid_group grid = cg::this_grid();
+  // mode 2: the whole grid is one cluster (<= 16 CTAs) -> hardware cluster barrier (release/acquire at cluster scope)
+  // instead of the cooperative grid barrier; mode 1: cooperative launch over the whole GPU
+  auto sync_all = [&]() { if (c.cluster_sync) cg::this_cluster().sync(); else grid.sync(); };
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
@@ -810,17 +814,17 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
     StepStats st = {0.f, 0.f};
     if (shared && c.adver) {
       general_stage<G, V>(c, s, 0, gid, ngroups, lane, mask, st);
-      grid.sync();
+      sync_all();
     }
     general_stage<G, V>(c, s, 1, gid, ngroups, lane, mask, st);
     fast_range<G, V, FULL>(c, s, ng, mid, gid, ngroups, lane, mask, st);
     if (shared) {
-      grid.sync();  // every H_Q contribution must have landed before the shared rows are updated
+      sync_all();  // every H_Q contribution must have landed before the shared rows are updated
       general_stage<G, V>(c, s, 2, gid, ngroups, lane, mask, st);
     }
     fast_range<G, V, FULL>(c, s, mid, nu, gid, ngroups, lane, mask, st);
     if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
-    grid.sync();
+    sync_all();
   }
 }
 
@@ -895,6 +899,30 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
       APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
     }
     APR_LAUNCH_CHECK();
+    return APR_OK;
+  }
+  if (mode == 2) {
+    // small batches (tables in L2, steps of a few microseconds): ONE cluster of up to 16 CTAs runs every step of the
+    // call; a cluster barrier costs a fraction of a microsecond where a kernel boundary or a grid barrier costs several
+    static const int cl_max = env_int("APR_CLUSTER_BLOCKS", 16);
+    const int grid = std::max(1, std::min(std::min(cl_max, 16), (c.B + gpb - 1) / gpb));
+    StepCtx cc = c;
+    cc.cluster_sync = 1;
+    if (grid > 8)
+      APR_CUDA_CHECK(cudaFuncSetAttribute(step_persistent_kernel<G, V, FULL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = grid;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    APR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, step_persistent_kernel<G, V, FULL>, cc));
     return APR_OK;
   }
   int occ = 0;
@@ -1074,7 +1102,7 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   memset(&c, 0, sizeof(c));
   c.Pb[0] = P; c.Qb[0] = Q; c.aPb[0] = accP; c.aQb[0] = accQ;
   c.GQb[0] = at<float>(ws, L.off_GQ); c.HQb[0] = at<float>(ws, L.off_HQ);
-  c.nranks = 1; c.rank = 0; c.rshift = 0; c.only_stage = -1;
+  c.nranks = 1; c.rank = 0; c.rshift = 0; c.only_stage = -1; c.cluster_sync = 0;
   c.d = d; c.B = B; c.S = S;
   c.lr = lr;
   // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
@@ -1099,7 +1127,7 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
                   apr_stream_t stream) {
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws);
   if (rc) return rc;
-  if (mode != 0 && mode != 1) return APR_E_ARG;
+  if (mode < 0 || mode > 2) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1116,7 +1144,7 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
                     apr_stream_t stream) {
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws);
   if (rc) return rc;
-  if (mode != 0 && mode != 1) return APR_E_ARG;
+  if (mode < 0 || mode > 2) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1197,7 +1225,7 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf);
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
-  c.s_begin = step; c.s_end = step + 1; c.only_stage = stage;
+  c.s_begin = step; c.s_end = step + 1; c.only_stage = stage; c.cluster_sync = 0;
   return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream));
 }
 

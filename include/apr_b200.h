@@ -76,7 +76,9 @@ int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_d
  *      with apr_train_workspace_init before first use (the kernels restore the zero invariant themselves).
  *      stats (nullable) receives per step {sum softplus(-r) of the PLAIN forward, count(x > 0)} as float[2].
  *      mode: 0 = one kernel launch per phase (3 per APR step, 2 per BPR step);
- *            1 = one persistent cooperative kernel for all n_steps (grid barriers between phases). */
+ *            1 = one persistent cooperative kernel for all n_steps (grid barriers between phases);
+ *            2 = the same persistent kernel launched as ONE thread-block cluster of <= 16 CTAs (cluster barriers between
+ *                phases): for small batches whose steps take a few microseconds (the reference's default B = 512). */
 int64_t apr_train_workspace_bytes(int32_t n_steps, int32_t batch, int32_t d);
 int apr_train_workspace_init(void* workspace, int64_t workspace_bytes, apr_stream_t stream);
 int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,

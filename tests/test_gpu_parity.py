@@ -72,7 +72,7 @@ def _run_cuda_steps(dev, P, Q, u, i, j, lr, reg, reg_adv, eps, adver, mode):
     return tP.cpu().numpy(), tQ.cpu().numpy(), aP.cpu().numpy(), aQ.cpu().numpy(), stats.cpu().numpy(), counts
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("adver", [0, 1])
 @pytest.mark.parametrize("d,U,I,S,B,zipf", [
     (64, 300, 200, 6, 512, False),     # reference batch size, heavy duplication

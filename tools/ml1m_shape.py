@@ -17,7 +17,7 @@ for u in range(U):
     eu.append(u); ei.append(int(it[0])); tu += [u] * cnt[u]; ti += it[1:].tolist()
 ds = ArrayDataset(np.asarray(tu), np.asarray(ti), np.asarray(eu), np.asarray(ei))
 print("pairs", len(tu), "users", ds.num_users, "items", ds.num_items)
-for mode in (0, 1):
+for mode in (0, 2):
     args = types.SimpleNamespace(embed_size=64, lr=0.05, reg=0.0, dns=1, adv="grad", eps=0.5, adver=0, reg_adv=1.0, epochs=0, seed=2019, batch_size=512, eval_mode="all")
     model = MF(ds.num_users, ds.num_items, args); model.build_graph()
     sess = Session(mode=mode); samples = sampling(ds); feed = init_eval_model(ds, args)
