@@ -542,7 +542,44 @@ def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
     bpr = run(args.batch, uniform, 32e6)
     bpr["note"] = "adver = 0: one forward/backward, Adagrad; same algorithmic bytes per triple as the APR step"
     hp = hp_apr
-    return {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z, "bpr_step": bpr}
+    out = {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z, "bpr_step": bpr}
+    out["sampler_epoch"] = bench_sampler(torch, engine, U, I, args.batch, dev)
+    return out
+
+
+def bench_sampler(torch, engine, U, I, B, dev, pairs=1 << 26):
+    """The epoch sampler (A8: APR.py:30-81) at the configs[3] scale: 2^26 training pairs of U users x I items, one
+    uniform negative per pair rejected against the user's sorted CSR row.  Counter-based (Feistel permutation + Philox),
+    so it is a pure streaming kernel: bytes = read one (u, i) pair (8) + write u, i, u_dns, j (16) + the CSR probes."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(2019)
+    pu = torch.randint(0, U, (pairs,), device=dev, dtype=torch.int32, generator=g)
+    pu, _ = torch.sort(pu)
+    pi = torch.randint(0, I, (pairs,), device=dev, dtype=torch.int32, generator=g)
+    # CSR of the train lists: rows sorted by item id (duplicates are harmless for the membership test)
+    key = pu.to(torch.int64) * I + pi.to(torch.int64)
+    key, _ = torch.sort(key)
+    cidx = (key % I).to(torch.int32)
+    counts = torch.bincount(pu, minlength=U)
+    cptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
+    cptr[1:] = torch.cumsum(counts, 0)
+    del key, counts
+    for ep in range(2):
+        out = engine.sample_epoch(pu, pi, B, I, cptr, cidx, 2019, ep, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for ep in range(reps):
+        out = engine.sample_epoch(pu, pi, B, I, cptr, cidx, 2019, 2 + ep, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    assert int(out[4].item()) == 0
+    n = (pairs // B) * B
+    return {"pairs": pairs, "batch": B, "ms_per_epoch": ms, "triples_per_s": n / (ms * 1e-3),
+            "stream_gb_per_s": 24.0 * n / (ms * 1e-3) / 1e9,
+            "note": "includes the output allocation of the call; 24 B/triple streamed + random CSR probes (HBM-latency bound)"}
 
 
 def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
