@@ -52,7 +52,7 @@ static inline int pow2ceil(int x) {
 struct TrainLayout {
   int S, B, d, Tu, Ti, Sc;
   int64_t off_hdr, off_GQ, off_HQ, off_GP, off_cbuf, off_ucnt, off_icnt, off_iall, off_nslow, off_nfast, off_tcursor,
-      off_seg_slow, off_seg_user, off_seg_off, off_seg_cnt, off_ucursor, off_entry, off_rec, off_seg_hdr, off_iu_item, off_tkey_u, off_tval_u,
+      off_npair, off_seg_slow, off_occ_cnt, off_occ_seg, off_pairs, off_seg_user, off_seg_off, off_seg_cnt, off_ucursor, off_entry, off_rec, off_seg_hdr, off_iu_item, off_tkey_u, off_tval_u,
       off_tkey_i, off_tval_i, total;
 };
 
@@ -76,7 +76,9 @@ static TrainLayout make_layout(int S, int B, int d) {
   L.off_nslow = take(int64_t(S) * 4);
   L.off_nfast = take(int64_t(S) * 4);
   L.off_tcursor = take(int64_t(S) * 4);
-  L.off_seg_slow = take(int64_t(S) * B * 4);
+  L.off_npair = take(int64_t(S) * 4);
+  L.off_seg_slow = take(int64_t(S) * B * 4);   // shared-item occurrences of the segment; -1 once it is part of a pair
+  L.off_occ_cnt = take(int64_t(S) * B * 4);    // occurrences of a shared slot (cleared with the counters above)
   L.off_seg_user = take(int64_t(S) * B * 4);
   L.off_seg_off = take(int64_t(S) * B * 4);
   L.off_seg_cnt = take(int64_t(S) * B * 4);
@@ -85,7 +87,9 @@ static TrainLayout make_layout(int S, int B, int d) {
   L.off_rec = take(int64_t(S) * B * 16);       // {i, j, slot_i, slot_j} in segment order
   L.off_seg_hdr = take(int64_t(S) * B * 32);   // per segment {user, b0, count, slow} + its first triple's record,
                                                // partitioned: slow segments first, then fast ones
-  L.off_iu_item = take(int64_t(S) * B * 4);    // shared slot -> item id
+  L.off_iu_item = take(int64_t(S) * B * 4);    // shared slot -> item id (sign bit set: slot handled by the pair path)
+  L.off_occ_seg = take(int64_t(S) * B * 8);    // first two segments that touch a shared slot
+  L.off_pairs = take(int64_t(S) * (B / 2 + 1) * 48);  // pair work units: {user_a, user_b, slot, 0}, rec_a, rec_b
   L.off_tkey_u = take(int64_t(L.Sc) * L.Tu * 4);
   L.off_tval_u = take(int64_t(L.Sc) * L.Tu * 4);
   L.off_tkey_i = take(int64_t(L.Sc) * L.Ti * 4);
@@ -96,6 +100,13 @@ static TrainLayout make_layout(int S, int B, int d) {
 
 template <typename T>
 static inline T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+static int env_int(const char* name, int dflt);
+// pair work units (prep_pair_kernel / pair_unit): rows of up to 128 floats (one float4 per lane), single GPU
+static bool pairs_enabled(int d) {
+  static const int on = env_int("APR_PAIRS", 1);
+  return on != 0 && d <= 128;
+}
 
 // ------------------------------------------------------------------------------------------------
 // prepare kernels (all steps of a sub-chunk in parallel; one hash table per step).  `s0` = first step of the
@@ -195,7 +206,7 @@ __global__ void prep_compact_kernel(int s0, int ns, int B, int Tu, int Ti, const
 __global__ void prep_scatter_kernel(const int32_t* __restrict__ i, const int32_t* __restrict__ j, int s0, int ns, int B,
                                     int Tu, int Ti, const int32_t* __restrict__ tval_u, const int32_t* __restrict__ tval_i,
                                     const int32_t* __restrict__ entry, const int32_t* __restrict__ seg_off,
-                                    int32_t* ucursor, int4* rec, int32_t* seg_slow) {
+                                    int32_t* ucursor, int4* rec, int32_t* seg_slow, int32_t* occ_cnt, int2* occ_seg) {
   const int64_t total = int64_t(ns) * B;
   for (int64_t tl = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; tl < total; tl += int64_t(gridDim.x) * blockDim.x) {
     const int sl = int(tl / B);
@@ -206,13 +217,57 @@ __global__ void prep_scatter_kernel(const int32_t* __restrict__ i, const int32_t
     const int sj = tval_i[int64_t(sl) * Ti + entry[3 * t + 2]];
     const int pos = seg_off[int64_t(s) * B + useg] + atomicAdd(&ucursor[int64_t(s) * B + useg], 1);
     rec[int64_t(s) * B + pos] = make_int4(i[t], j[t], si, sj);
-    if (si >= 0 || sj >= 0) seg_slow[int64_t(s) * B + useg] = 1;
+    const int nsh = (si >= 0 ? 1 : 0) + (sj >= 0 ? 1 : 0);
+    if (nsh) {
+      atomicAdd(&seg_slow[int64_t(s) * B + useg], nsh);
+      // the first two segments that touch a shared slot (pair detection); a triple with i == j registers twice
+      if (occ_cnt && si >= 0) {
+        const int k = atomicAdd(&occ_cnt[int64_t(s) * B + si], 1);
+        if (k < 2) reinterpret_cast<int32_t*>(&occ_seg[int64_t(s) * B + si])[k] = useg;
+      }
+      if (occ_cnt && sj >= 0) {
+        const int k = atomicAdd(&occ_cnt[int64_t(s) * B + sj], 1);
+        if (k < 2) reinterpret_cast<int32_t*>(&occ_seg[int64_t(s) * B + sj])[k] = useg;
+      }
+    }
+  }
+}
+
+// PAIR detection, one thread per shared slot.  In a uniform batch ~97 % of the shared items occur exactly twice, in two
+// different single-triple segments that have no other shared item: such a component of two segments is one PAIR work
+// unit, processed by one group entirely in registers (pair_unit) -- no workspace slot, no RED, no stage split.  Each
+// eligible segment has exactly ONE shared occurrence, so it belongs to at most one slot: no two threads claim it.
+__global__ void prep_pair_kernel(int s0, int ns, int B, const int32_t* __restrict__ icnt,
+                                 const int32_t* __restrict__ occ_cnt, const int2* __restrict__ occ_seg,
+                                 const int32_t* __restrict__ seg_user, const int32_t* __restrict__ seg_off,
+                                 const int32_t* __restrict__ seg_cnt, int32_t* seg_slow, const int4* __restrict__ rec,
+                                 int32_t* iu_item, int32_t* npair, int4* pairs) {
+  const int64_t total = int64_t(ns) * B;
+  for (int64_t tl = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; tl < total; tl += int64_t(gridDim.x) * blockDim.x) {
+    const int s = s0 + int(tl / B);
+    const int slot = int(tl - int64_t(s - s0) * B);
+    if (slot >= icnt[s]) continue;
+    const int64_t b = int64_t(s) * B;
+    if (occ_cnt[b + slot] != 2) continue;
+    const int2 ab = occ_seg[b + slot];
+    if (ab.x == ab.y) continue;                                   // i == j inside one triple
+    if (seg_cnt[b + ab.x] != 1 || seg_cnt[b + ab.y] != 1) continue;
+    if (seg_slow[b + ab.x] != 1 || seg_slow[b + ab.y] != 1) continue;
+    const int k = atomicAdd(&npair[s], 1);
+    int4* out = pairs + (int64_t(s) * (B / 2 + 1) + k) * 3;
+    out[0] = make_int4(seg_user[b + ab.x], seg_user[b + ab.y], slot, 0);
+    out[1] = rec[b + seg_off[b + ab.x]];
+    out[2] = rec[b + seg_off[b + ab.y]];
+    seg_slow[b + ab.x] = -1;
+    seg_slow[b + ab.y] = -1;
+    iu_item[b + slot] |= int32_t(0x80000000u);                    // stage 2 skips this slot
   }
 }
 
 // one thread per segment: packed 32-byte header, written in PARTITIONED order -- GENERAL segments (touching a shared
-// item, or holding several triples of one user) occupy [0, ngen), FAST ones (one triple, both items singletons)
-// [ngen, nu) -- so each kernel walks a dense range.  header.w = 1 iff the segment touches a shared item.
+// item, or holding several triples of one user) occupy [0, ngen), FAST ones (one triple, both items singletons) the
+// END of the range, [nu - nfast, nu); the 2 npair segments taken by pair work units get no header (the gap between the
+// two) -- so each kernel walks a dense range.  header.w != 0 iff the segment touches a shared item.
 __global__ void prep_pack_kernel(int s0, int ns, int B, const int32_t* __restrict__ ucnt,
                                  const int32_t* __restrict__ seg_user, const int32_t* __restrict__ seg_off,
                                  const int32_t* __restrict__ seg_cnt, const int32_t* __restrict__ seg_slow,
@@ -227,6 +282,7 @@ __global__ void prep_pack_kernel(int s0, int ns, int B, const int32_t* __restric
     if (valid) { s = s0 + int(tl / B); seg = int(tl - int64_t(s - s0) * B); nu = ucnt[s]; valid = seg < nu; }
     const int64_t t = int64_t(s) * B + seg;
     const int shared = valid ? seg_slow[t] : 0;
+    if (shared < 0) valid = false;   // part of a pair: neither in the general nor in the fast range
     int b0 = 0, b1 = 0;
     if (valid) { b0 = seg_off[t]; b1 = b0 + seg_cnt[t]; }
     const int slow = (shared || (b1 - b0) != 1) ? 1 : 0;
@@ -274,6 +330,8 @@ struct StepCtx {
   float lr, kreg, reg_adv, eps;
   int adver;
   const int32_t* ucnt; const int32_t* icnt; const int32_t* nslow;
+  const int32_t* npair;   // nullable: pair work units per step (segments [nslow, nslow + 2 npair) are theirs)
+  const int4* pairs;
   const int4* seg_hdr; const int4* rec; const int32_t* iu_item;
   float* GP; float* cbuf;
   float* stats;  // nullable [S,2]
@@ -716,6 +774,7 @@ __device__ __forceinline__ void items_shared(const StepCtx& c, int s, int gid, i
   row_zero<G, V>(z);
   for (int slot = gid * c.nranks + c.rank; slot < ni; slot += ngroups * c.nranks) {
     const int item = iu_item[slot];
+    if (item < 0) continue;   // slot of a pair work unit: updated there
     Row<G, V> w, g, a;
     row_load<G, V>(g, HQ_ROW(c, slot), lane, d);
     row_load<G, V>(w, Q_ROW(c, item), lane, d);
@@ -723,6 +782,132 @@ __device__ __forceinline__ void items_shared(const StepCtx& c, int s, int gid, i
     adagrad_apply<G, V>(Q_ROW(c, item), AQ_ROW(c, item), w, a, g, lane, d, c.lr);
     row_store<G, V>(z, HQ_ROW(c, slot), lane, d);
     if (c.adver) row_store<G, V>(z, GQ_ROW(c, slot), lane, d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PAIR work unit: two single-triple segments a, b whose only coupling to the rest of the batch is ONE item that occurs
+// in both (and nowhere else).  Everything the three-stage general path does through the workspace -- the batch-wide
+// gradient sum of the shared item, its Delta, its total gradient -- is a two-term sum here, so one group does both
+// triples in registers: 6 row reads (the shared row twice), 5 accumulator reads, 10 row writes.
+// Same formulas as slow_plain / adv_triple / item_sink (APR.py:143-165,180-195), per occurrence.
+template <int G, int V>
+__device__ __forceinline__ void pair_unit(const StepCtx& c, const int4 ph, const int4 ra, const int4 rb, int lane,
+                                          unsigned mask, StepStats& st) {
+  const int d = c.d;
+  const int slot = ph.z;
+  const bool sa = ra.z == slot, sb = rb.z == slot;      // shared item is the POSITIVE of a / of b (else the negative)
+  float* Pa = P_ROW(c, ph.x);
+  float* Pb = P_ROW(c, ph.y);
+  float* Qa = Q_ROW(c, ra.x);
+  float* Na = Q_ROW(c, ra.y);
+  float* Qb = Q_ROW(c, rb.x);
+  float* Nb = Q_ROW(c, rb.y);
+  const int item_s = sa ? ra.x : ra.y, item_oa = sa ? ra.y : ra.x, item_ob = sb ? rb.y : rb.x;
+  Row<G, V> pa, pb, qa, na, qb, nb, aPa, aPb, aS, aOa, aOb;
+  row_load<G, V>(pa, Pa, lane, d);
+  row_load<G, V>(pb, Pb, lane, d);
+  row_load<G, V>(qa, Qa, lane, d);
+  row_load<G, V>(na, Na, lane, d);
+  row_load<G, V>(qb, Qb, lane, d);
+  row_load<G, V>(nb, Nb, lane, d);
+  row_load<G, V>(aPa, AP_ROW(c, ph.x), lane, d);
+  row_load<G, V>(aPb, AP_ROW(c, ph.y), lane, d);
+  row_load<G, V>(aS, AQ_ROW(c, item_s), lane, d);
+  row_load<G, V>(aOa, AQ_ROW(c, item_oa), lane, d);
+  row_load<G, V>(aOb, AQ_ROW(c, item_ob), lane, d);
+
+  const float xa = row_dot<G, V>(pa, qa, mask) - row_dot<G, V>(pa, na, mask);
+  const float xb = row_dot<G, V>(pb, qb, mask) - row_dot<G, V>(pb, nb, mask);
+  float r0, r1;
+  const float ca = bpr_coeff(xa, r0), cb = bpr_coeff(xb, r1);
+  if (c.stats) {
+    st.loss += softplus_neg(r0) + softplus_neg(r1);
+    st.correct += ((xa > 0.f) ? 1.f : 0.f) + ((xb > 0.f) ? 1.f : 0.f);
+  }
+  Row<G, V> ga, gb, hia, hja, hib, hjb;   // user-row gradients; per-occurrence item gradients (pos / neg of a and b)
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    ga.v[k] = f4_scale(f4_sub(qa.v[k], na.v[k]), ca);
+    gb.v[k] = f4_scale(f4_sub(qb.v[k], nb.v[k]), cb);
+  }
+  if (!c.adver) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      ga.v[k] = f4_fma(c.kreg, pa.v[k], ga.v[k]);
+      gb.v[k] = f4_fma(c.kreg, pb.v[k], gb.v[k]);
+      hia.v[k] = f4_fma(c.kreg, qa.v[k], f4_scale(pa.v[k], ca));
+      hja.v[k] = f4_fma(c.kreg, na.v[k], f4_scale(pa.v[k], -ca));
+      hib.v[k] = f4_fma(c.kreg, qb.v[k], f4_scale(pb.v[k], cb));
+      hjb.v[k] = f4_fma(c.kreg, nb.v[k], f4_scale(pb.v[k], -cb));
+    }
+  } else {
+    // plain gradient sum of the shared item over its two occurrences, and the three Delta scales that involve sums
+    Row<G, V> gs;
+#pragma unroll
+    for (int k = 0; k < V; ++k) gs.v[k] = f4_fma(sb ? cb : -cb, pb.v[k], f4_scale(pa.v[k], sa ? ca : -ca));
+    const float scs = delta_scale<G, V>(gs, c.eps, mask);
+    const float spa = delta_scale<G, V>(ga, c.eps, mask), spb = delta_scale<G, V>(gb, c.eps, mask);
+    // singleton occurrences: G = +-c p, so Delta = eps c p rsqrt(max(c^2 |p|^2, 1e-12))
+    Row<G, V> t;
+#pragma unroll
+    for (int k = 0; k < V; ++k) t.v[k] = f4_scale(pa.v[k], ca);
+    const float soa = delta_scale<G, V>(t, c.eps, mask);
+#pragma unroll
+    for (int k = 0; k < V; ++k) t.v[k] = f4_scale(pb.v[k], cb);
+    const float sob = delta_scale<G, V>(t, c.eps, mask);
+    Row<G, V> pda, pdb, qda, nda, qdb, ndb;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      pda.v[k] = f4_fma(spa, ga.v[k], pa.v[k]);
+      pdb.v[k] = f4_fma(spb, gb.v[k], pb.v[k]);
+      // Delta of an occurrence: the shared item's from gs, a singleton's from its own +-c p
+      qda.v[k] = sa ? f4_fma(scs, gs.v[k], qa.v[k]) : f4_fma(soa * ca, pa.v[k], qa.v[k]);
+      nda.v[k] = sa ? f4_fma(-soa * ca, pa.v[k], na.v[k]) : f4_fma(scs, gs.v[k], na.v[k]);
+      qdb.v[k] = sb ? f4_fma(scs, gs.v[k], qb.v[k]) : f4_fma(sob * cb, pb.v[k], qb.v[k]);
+      ndb.v[k] = sb ? f4_fma(-sob * cb, pb.v[k], nb.v[k]) : f4_fma(scs, gs.v[k], nb.v[k]);
+    }
+    const float xaa = row_dot<G, V>(pda, qda, mask) - row_dot<G, V>(pda, nda, mask);
+    const float xab = row_dot<G, V>(pdb, qdb, mask) - row_dot<G, V>(pdb, ndb, mask);
+    float r2, r3;
+    const float caa = c.reg_adv * bpr_coeff(xaa, r2), cab = c.reg_adv * bpr_coeff(xab, r3);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      ga.v[k] = f4_fma(caa, f4_sub(qda.v[k], nda.v[k]), ga.v[k]);
+      ga.v[k] = f4_fma(c.kreg, pa.v[k], ga.v[k]);
+      gb.v[k] = f4_fma(cab, f4_sub(qdb.v[k], ndb.v[k]), gb.v[k]);
+      gb.v[k] = f4_fma(c.kreg, pb.v[k], gb.v[k]);
+      const float4 ta = f4_fma(caa, pda.v[k], f4_scale(pa.v[k], ca));   // c p + reg_adv c' (p + dP)
+      const float4 tb = f4_fma(cab, pdb.v[k], f4_scale(pb.v[k], cb));
+      hia.v[k] = f4_fma(c.kreg, qa.v[k], ta);
+      hja.v[k] = f4_fma(c.kreg, na.v[k], f4_scale(ta, -1.f));
+      hib.v[k] = f4_fma(c.kreg, qb.v[k], tb);
+      hjb.v[k] = f4_fma(c.kreg, nb.v[k], f4_scale(tb, -1.f));
+    }
+  }
+  // total gradient of the shared item = its two occurrences; the other item of each triple keeps its own
+  Row<G, V> hs;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float4 ua = sa ? hia.v[k] : hja.v[k], ub = sb ? hib.v[k] : hjb.v[k];
+    hs.v[k] = make_float4(ua.x + ub.x, ua.y + ub.y, ua.z + ub.z, ua.w + ub.w);
+  }
+  adagrad_apply<G, V>(Pa, AP_ROW(c, ph.x), pa, aPa, ga, lane, d, c.lr);
+  adagrad_apply<G, V>(Pb, AP_ROW(c, ph.y), pb, aPb, gb, lane, d, c.lr);
+  adagrad_apply<G, V>(sa ? Na : Qa, AQ_ROW(c, item_oa), sa ? na : qa, aOa, sa ? hja : hia, lane, d, c.lr);
+  adagrad_apply<G, V>(sb ? Nb : Qb, AQ_ROW(c, item_ob), sb ? nb : qb, aOb, sb ? hjb : hib, lane, d, c.lr);
+  adagrad_apply<G, V>(sa ? Qa : Na, AQ_ROW(c, item_s), sa ? qa : na, aS, hs, lane, d, c.lr);
+}
+
+template <int G, int V>
+__device__ __forceinline__ void pair_range(const StepCtx& c, int s, int gid, int ngroups, int lane, unsigned mask,
+                                           StepStats& st) {
+  if (!c.npair) return;
+  const int np = c.npair[s];
+  const int4* pairs = c.pairs + int64_t(s) * (c.B / 2 + 1) * 3;
+  for (int k = gid; k < np; k += ngroups) {
+    const int4 ph = __ldg(&pairs[3 * k]), ra = __ldg(&pairs[3 * k + 1]), rb = __ldg(&pairs[3 * k + 2]);
+    pair_unit<G, V>(c, ph, ra, rb, lane, mask, st);
   }
 }
 
@@ -792,7 +977,18 @@ __global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fas
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
   StepStats st = {0.f, 0.f};
-  fast_range<G, V, FULL>(c, s, c.nslow[s], c.ucnt[s], gid, ngroups, lane, group_mask<G>(), st);
+  fast_range<G, V, FULL>(c, s, c.nslow[s] + (c.npair ? 2 * c.npair[s] : 0), c.ucnt[s], gid, ngroups, lane, group_mask<G>(), st);
+  if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+}
+
+// mode 0: the pair work units of one step (third stream; touches rows no other kernel of the step touches)
+template <int G, int V>
+__global__ void __launch_bounds__(kThreads, 2) pair_kernel(StepCtx c, int s) {
+  const int lane = threadIdx.x % G;
+  const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
+  const int ngroups = gridDim.x * (kThreads / G);
+  StepStats st = {0.f, 0.f};
+  pair_range<G, V>(c, s, gid, ngroups, lane, group_mask<G>(), st);
   if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
 }
 
@@ -808,7 +1004,7 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
   const int ngroups = gridDim.x * (kThreads / G);
   const unsigned mask = group_mask<G>();
   for (int s = c.s_begin; s < c.s_end; ++s) {
-    const int nu = c.ucnt[s], ng = c.nslow[s];
+    const int nu = c.ucnt[s], ng = c.nslow[s] + (c.npair ? 2 * c.npair[s] : 0);   // ng: first fast segment
     const bool shared = c.icnt[s] > 0;  // grid-uniform
     const int mid = ng + (nu - ng + 1) / 2;
     StepStats st = {0.f, 0.f};
@@ -817,6 +1013,7 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
       sync_all();
     }
     general_stage<G, V>(c, s, 1, gid, ngroups, lane, mask, st);
+    if constexpr (V == 1) pair_range<G, V>(c, s, gid, ngroups, lane, mask, st);   // independent of every other segment
     fast_range<G, V, FULL>(c, s, ng, mid, gid, ngroups, lane, mask, st);
     if (shared) {
       sync_all();  // every H_Q contribution must have landed before the shared rows are updated
@@ -831,6 +1028,8 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
 // second stream + events for the fork/join of mode 0 (created once per process; no device memory)
 struct AuxStream {
   cudaStream_t stream = nullptr;       // fast-path kernels of mode 0
+  cudaStream_t pair_stream = nullptr;  // pair work units of mode 0
+  cudaEvent_t join2 = nullptr;
   cudaStream_t prep_stream = nullptr;  // index preparation, pipelined one sub-chunk ahead of the step kernels
   cudaEvent_t fork = nullptr, join = nullptr, entry = nullptr;
   std::vector<cudaEvent_t> prep_done;
@@ -853,6 +1052,8 @@ static AuxStream& aux_stream() {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
         cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+        cudaStreamCreateWithPriority(&a.pair_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+        cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming) == cudaSuccess)
@@ -888,15 +1089,23 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
       APR_LAUNCH_CHECK();
       return APR_OK;
     }
+    const bool pairs = V == 1 && c.npair != nullptr;
+    const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
     for (int s = c.s_begin; s < c.s_end; ++s) {
       APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
       APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
       fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.stream>>>(c, s);
       APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+      if (pairs) {
+        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
+        if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(c, s);
+        APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
+      }
       if (c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 0);
       general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 1);
       general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 2);
       APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
+      if (pairs) APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join2, 0));
     }
     APR_LAUNCH_CHECK();
     return APR_OK;
@@ -1000,8 +1209,9 @@ static int run_loss_acc(const float* P, const float* Q, int d, const int32_t* u,
 }
 
 // index preparation of the steps [s0, s0+ns) (one L2-sized sub-chunk) on stream st
+// `pairs`: also detect pair work units (single-GPU drivers, d <= 128); the sharded driver does not use them
 static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, const TrainLayout& L, int s0, int ns,
-                       int64_t rows_p, int64_t rows_q, void* ws, cudaStream_t st) {
+                       int64_t rows_p, int64_t rows_q, void* ws, cudaStream_t st, bool pairs) {
   const int B = L.B;
   int32_t* tkey_u = at<int32_t>(ws, L.off_tkey_u);
   int32_t* tval_u = at<int32_t>(ws, L.off_tval_u);
@@ -1028,7 +1238,16 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
       at<int32_t>(ws, L.off_iu_item));
   prep_scatter_kernel<<<grid_a, threads, 0, st>>>(i, j, s0, ns, B, L.Tu, L.Ti, tval_u, tval_i, at<int32_t>(ws, L.off_entry),
                                                   at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_ucursor),
-                                                  at<int4>(ws, L.off_rec), at<int32_t>(ws, L.off_seg_slow));
+                                                  at<int4>(ws, L.off_rec), at<int32_t>(ws, L.off_seg_slow),
+                                                  pairs ? at<int32_t>(ws, L.off_occ_cnt) : nullptr,
+                                                  at<int2>(ws, L.off_occ_seg));
+  if (pairs)
+    prep_pair_kernel<<<grid_a, threads, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_icnt), at<int32_t>(ws, L.off_occ_cnt),
+                                                 at<int2>(ws, L.off_occ_seg), at<int32_t>(ws, L.off_seg_user),
+                                                 at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
+                                                 at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
+                                                 at<int32_t>(ws, L.off_iu_item), at<int32_t>(ws, L.off_npair),
+                                                 at<int4>(ws, L.off_pairs));
   prep_pack_kernel<<<grid_a, threads, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_seg_user),
                                                at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
                                                at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
@@ -1058,7 +1277,7 @@ static int prepare_impl(const int32_t* u, const int32_t* i, const int32_t* j, in
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   int rc = prepare_clear(L, ws, st);
   for (int s0 = 0; s0 < S && !rc; s0 += L.Sc)
-    rc = prepare_sub(u, i, j, L, s0, std::min(L.Sc, S - s0), rows_p, rows_q, ws, st);
+    rc = prepare_sub(u, i, j, L, s0, std::min(L.Sc, S - s0), rows_p, rows_q, ws, st, pairs_enabled(d));
   return rc;
 }
 
@@ -1110,6 +1329,8 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
   c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt);
   c.nslow = at<int32_t>(ws, L.off_nslow);
+  c.npair = pairs_enabled(d) ? at<int32_t>(ws, L.off_npair) : nullptr;
+  c.pairs = at<int4>(ws, L.off_pairs);
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr);
   c.rec = at<int4>(ws, L.off_rec);
   c.iu_item = at<int32_t>(ws, L.off_iu_item);
@@ -1159,7 +1380,7 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   const int nsub = (S + L.Sc - 1) / L.Sc;
   for (int k = 0; k < nsub; ++k) {
     const int s0 = k * L.Sc, ns = std::min(L.Sc, S - s0);
-    rc = prepare_sub(u, i, j, L, s0, ns, rows_p, rows_q, ws, ax.prep_stream);
+    rc = prepare_sub(u, i, j, L, s0, ns, rows_p, rows_q, ws, ax.prep_stream, pairs_enabled(d));
     if (rc) return rc;
     cudaEvent_t e = ax.prep_event(size_t(k));
     if (!e) return APR_E_CUDA;
@@ -1192,7 +1413,7 @@ int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = clear_counters ? prepare_clear_range(L, ws, s0, ns, st) : APR_OK;
-  for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st);
+  for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st, false);
   return rc;
 }
 
