@@ -189,7 +189,7 @@ def workload_config(args):
     return {"workload": "BASELINE.json configs[3]: synthetic %dM users x %dM items, d=%d, APR step (eps 0.5, reg_adv 1, "
                         "lr 0.05, Adagrad), uniform triples" % (args.users // 10 ** 6, args.items // 10 ** 6, args.dim),
             "users": args.users, "items": args.items, "d": args.dim, "batch_per_step": args.batch,
-            "step_mode": "persistent-cooperative" if args.mode == 1 else "fast-kernel || general-stages (2 streams)",
+            "step_mode": {1: "persistent-cooperative", 2: "persistent, one thread-block cluster"}.get(args.mode, "fast kernel || pair kernel || general stages (3 streams)"),
             "cache": "inputs larger than L2 (tables %.1f GB vs 126 MB L2)" %
                      (2 * 4 * args.dim * (args.users + args.items) / 1e9)}
 
@@ -397,10 +397,14 @@ def main_single(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * K * B / (ms * 1e-3)
-    def n_launches(S):  # 5 index-preparation kernels per L2-sized sub-chunk + the step kernels (csrc/train.cu)
+    pairs_on = d <= 128 and os.environ.get("APR_PAIRS", "1") != "0"   # pair work units (csrc/train.cu: pairs_enabled)
+
+    def n_launches(S):  # index-preparation kernels per L2-sized sub-chunk + the step kernels (csrc/train.cu)
         p2 = 1 << max(0, (B - 1).bit_length())
         sc = max(1, min(S, (48 << 20) // ((max(32, 2 * p2) + max(32, 4 * p2)) * 8)))
-        return 4 * -(-S // sc) + (1 if args.mode == 1 else 4 * S)
+        prep = 5 if pairs_on else 4      # insert, compact, scatter, [pair detection], pack
+        step = 5 if pairs_on else 4      # fast kernel, [pair kernel], three general stages
+        return prep * -(-S // sc) + (1 if args.mode in (1, 2) else step * S)
     launches = sum(n_launches(c[0].shape[0]) for c in chunks)
 
     # ---- roofline of the dominant kernel(s): the embedding step kernels, index preparation excluded -------
@@ -420,11 +424,14 @@ def main_single(args):
         bytes_total += float(16 * d * cnt.sum() + 12 * B * c[0].shape[0])
     achieved = bytes_total / (ms_run * 1e-3) / 1e9
     steps_roof = sum(c[0].shape[0] for c in chunks[:n_roof])
-    # traffic: dram__bytes_read+write per step from the ncu capture of this command (profiles/r1f_launches_mode0_B65536.csv:
-    # fast_kernel 177+116 MB, 3 general stages ~16 MB each; serialised cold-cache replay, late write-backs not attributed)
+    # traffic: dram__bytes_read+write per step from the ncu capture of this command (profiles/r1m_launches_mode0_B65536_pairs.csv:
+    # fast_kernel 177.2 + 114.3 MB, pair_kernel 18.1 MB, 3 general stages 2.5 MB each; serialised cold-cache replay, the
+    # late write-backs of the small kernels are not attributed to them)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 340.7e6 if (B == 65536 and d == 128 and args.mode == 0) else None, "peak_kind": peak_kind,
-                "kernel": "step_persistent_kernel<32,1,true>" if args.mode == 1 else "fast_kernel<32,1,true> || 3 x general_stage_kernel<32,1> per step",
+                "traffic": 317.1e6 if (B == 65536 and d == 128 and args.mode == 0 and pairs_on) else None, "peak_kind": peak_kind,
+                "kernel": "step_persistent_kernel" if args.mode in (1, 2) else
+                ("fast_kernel || pair_kernel || 3 x general_stage_kernel per step" if pairs_on else
+                 "fast_kernel || 3 x general_stage_kernel per step"),
                 "bytes_per_step_model": bytes_total / steps_roof, "ms_per_step_kernel": ms_run / steps_roof}
 
     # ---- e2e: public API with HOST batches; H2D of ids and D2H of the per-step loss inside the region ------
