@@ -1400,6 +1400,7 @@ int apr_train_layout(int32_t S, int32_t B, int32_t d, int64_t* out) {
   const TrainLayout L = make_layout(S, B, d);
   out[0] = L.total; out[1] = L.Sc; out[2] = L.off_ucnt; out[3] = L.off_icnt; out[4] = L.off_iall; out[5] = L.off_nslow;
   out[6] = L.off_seg_hdr; out[7] = L.off_rec; out[8] = L.off_iu_item; out[9] = L.off_hdr;
+  out[10] = L.off_npair; out[11] = L.off_nfast;
   return APR_OK;
 }
 

@@ -4,6 +4,8 @@ Bars (BASELINE.json north_star): sampled indices, rank positions and top-K ids b
 embeddings within 1e-5 relative in fp32.  "Relative" for a tensor means |a-b| <= RTOL * max|ref| element-wise
 (sums of signed terms cancel, so a per-element relative bound is not meaningful for fp32 atomics).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -66,6 +68,8 @@ def _run_cuda_steps(dev, P, Q, u, i, j, lr, reg, reg_adv, eps, adver, mode):
                        reg, reg_adv, eps, adver, ws, mode=mode, stats=stats)
     torch.cuda.synchronize()
     counts = ws.unique_counts(S)
+    L = engine.train_layout(S, B, P.shape[1])
+    _run_cuda_steps.last_npair = ws.buf[L["npair"]:L["npair"] + 4 * S].view(torch.int32).cpu().numpy().copy()
     # the workspace must be back to its all-zero invariant (shared-item G_Q / H_Q slots re-zeroed by phase C)
     rows_bytes = (B * P.shape[1] * 4 + 255) // 256 * 256
     assert int(ws.buf[256:256 + 2 * rows_bytes].count_nonzero().item()) == 0
@@ -100,6 +104,49 @@ def test_train_steps_match_oracle(cuda_device, mode, adver, d, U, I, S, B, zipf)
     for s in range(S):  # exact unique-row counts feed the roofline byte model
         assert counts[s, 0] == np.unique(u[s]).size
         assert counts[s, 1] == np.unique(np.concatenate([i[s], j[s]])).size
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("adver", [0, 1])
+@pytest.mark.parametrize("d", [64, 128, 24])
+def test_pair_work_units_match_oracle(cuda_device, mode, adver, d):
+    """Hand-built batch that exercises the PAIR path (csrc/train.cu: prep_pair_kernel / pair_unit) in every role --
+    the twice-occurring item positive in both triples, negative in both, positive in one and negative in the other --
+    next to everything that must NOT become a pair: an item occurring three times, a segment with two shared items, a
+    user with two triples, i == j inside one triple, and plain singleton (fast-path) triples.  Two steps, so the second
+    one reads what the first one wrote."""
+    U, I = 64, 200
+    rng = np.random.RandomState(d)
+    P = (rng.randn(U, d) * 0.1).astype(np.float32)
+    Q = (rng.randn(I, d) * 0.1).astype(np.float32)
+    step = [
+        (0, 10, 11), (1, 10, 12),        # item 10: pos / pos            -> pair
+        (2, 13, 14), (3, 15, 14),        # item 14: neg / neg            -> pair
+        (4, 16, 17), (5, 18, 16),        # item 16: pos / neg            -> pair
+        (6, 20, 21), (7, 20, 22), (8, 23, 20),   # item 20 three times   -> general
+        (9, 30, 31), (10, 30, 32), (11, 33, 31),  # segment 9 has two shared items -> general (30 and 31 occur twice)
+        (12, 40, 41), (12, 42, 40),      # user 12 twice, item 40 twice  -> general
+        (13, 50, 50),                    # i == j                        -> general (one segment registers twice)
+        (14, 60, 61), (15, 62, 63), (16, 64, 65),   # singletons          -> fast path
+        (17, 70, 71), (18, 72, 70),      # item 70: pos / neg            -> pair
+    ]
+    B = len(step)
+    u = np.asarray([[t[0] for t in step], [t[0] for t in reversed(step)]], np.int32)
+    i = np.asarray([[t[1] for t in step], [t[1] for t in reversed(step)]], np.int32)
+    j = np.asarray([[t[2] for t in step], [t[2] for t in reversed(step)]], np.int32)
+    assert u.shape == (2, B)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 1.0, 0.5
+    rP, rQ, raP, raQ, rstats = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, adver)
+    gP, gQ, gaP, gaQ, gstats, counts = _run_cuda_steps(cuda_device, P, Q, u, i, j, lr, reg, reg_adv, eps, adver, mode)
+    # items 10, 14, 16 and 70 make pairs; 20, 30/31, 40, 50 must not
+    want_pairs = 0 if os.environ.get("APR_PAIRS", "1") == "0" else 4
+    assert _run_cuda_steps.last_npair.tolist() == [want_pairs, want_pairs]
+    _close(gP, rP)
+    _close(gQ, rQ)
+    _close(gaP, raP)
+    _close(gaQ, raQ)
+    _close(gstats[:, 0], rstats[:, 0])
+    assert np.array_equal(gstats[:, 1].astype(np.int64), rstats[:, 1].astype(np.int64))
 
 
 def test_train_step_single_triple_and_self_pair(cuda_device):
