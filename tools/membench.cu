@@ -1,6 +1,7 @@
-// Ceiling probe for the APR step's memory pattern on B200: per "segment" one warp reads 6 random 512-byte rows
+// Ceiling probe for the APR step's memory pattern on B200: per "segment" one lane group reads 6 random rows of D floats
 // (P[u], accP[u], Q[i], accQ[i], Q[j], accQ[j]) and writes all 6 back.  Variants isolate what limits throughput.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/membench tools/membench.cu && tools/membench
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 [-DROWD=64] -o tools/membench tools/membench.cu && tools/membench
+// ROWD = floats per row (default 128 = 512-byte rows, one warp per segment; 64 = 256-byte rows, two segments per warp)
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -9,14 +10,18 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1);} } while (0)
 
-constexpr int D = 128;
+#ifndef ROWD
+#define ROWD 128
+#endif
+constexpr int D = ROWD;
+constexpr int G = D / 4;   // lanes per row (one float4 each)
 
 template <int MODE>  // 0: read only; 1: read+write; 2: read+write with ~reduction chain; 3: read+write, 2 segments in flight
 __global__ void __launch_bounds__(256) probe(float* P, float* A, float* Q, float* AQ, const int4* __restrict__ ids, int n,
                                              float* sink) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x % G;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / G;     // lane-group index
+  const int nwarps = (gridDim.x * blockDim.x) / G;
   float acc = 0.f;
   for (int s = warp; s < n; s += nwarps) {
     const int4 t = __ldg(&ids[s]);
@@ -32,7 +37,7 @@ __global__ void __launch_bounds__(256) probe(float* P, float* A, float* Q, float
 #pragma unroll
       for (int rep = 0; rep < 6; ++rep) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         x = x * 0.5f + p.z;
       }
     }
@@ -76,8 +81,8 @@ int main() {
       cudaEventRecord(e1);
       CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-      const double bytes = double(n) * 6 * 512 * (mode == 0 ? 1 : 2);
-      printf("mode %d  warps/SM %2d  %.3f ms  %.0f GB/s  (%.1f ns/segment-chip)\n", mode, bl / 148 * 8, ms, bytes / ms / 1e6,
+      const double bytes = double(n) * 6 * (D * 4) * (mode == 0 ? 1 : 2);
+      printf("row %d B  mode %d  warps/SM %2d  %.3f ms  %.0f GB/s  (%.1f ns/segment-chip)\n", D * 4, mode, bl / 148 * 8, ms, bytes / ms / 1e6,
              ms * 1e6 / n);
     }
   return 0;
