@@ -906,7 +906,9 @@ __device__ __forceinline__ void pair_range(const StepCtx& c, int s, int gid, int
   const int np = c.npair[s];
   const int4* pairs = c.pairs + int64_t(s) * (c.B / 2 + 1) * 3;
   for (int k = gid; k < np; k += ngroups) {
-    const int4 ph = __ldg(&pairs[3 * k]), ra = __ldg(&pairs[3 * k + 1]), rb = __ldg(&pairs[3 * k + 2]);
+    const int4 ph = __ldg(&pairs[3 * k]);
+    if (c.nranks > 1 && (ph.x & (c.nranks - 1)) != c.rank) continue;   // sharded tables: the owner of user a does the pair
+    const int4 ra = __ldg(&pairs[3 * k + 1]), rb = __ldg(&pairs[3 * k + 2]);
     pair_unit<G, V>(c, ph, ra, rb, lane, mask, st);
   }
 }
@@ -1084,7 +1086,11 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
     if (c.only_stage >= 0) {
       for (int s = c.s_begin; s < c.s_end; ++s) {
         if (c.only_stage == 3) fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, st>>>(c, s);
-        else if (c.only_stage > 0 || c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, c.only_stage);
+        else if (c.only_stage == 4) {
+          if constexpr (V == 1) {
+            if (c.npair) pair_kernel<G, V><<<std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms)), kThreads, 0, st>>>(c, s);
+          }
+        } else if (c.only_stage > 0 || c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, c.only_stage);
       }
       APR_LAUNCH_CHECK();
       return APR_OK;
@@ -1209,7 +1215,7 @@ static int run_loss_acc(const float* P, const float* Q, int d, const int32_t* u,
 }
 
 // index preparation of the steps [s0, s0+ns) (one L2-sized sub-chunk) on stream st
-// `pairs`: also detect pair work units (single-GPU drivers, d <= 128); the sharded driver does not use them
+// `pairs`: also detect pair work units (d <= 128)
 static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, const TrainLayout& L, int s0, int ns,
                        int64_t rows_p, int64_t rows_q, void* ws, cudaStream_t st, bool pairs) {
   const int B = L.B;
@@ -1265,9 +1271,10 @@ static int prepare_clear(const TrainLayout& L, void* ws, cudaStream_t st) {
 
 // the same for the steps [s0, s0+ns) only (other steps' arrays may already hold another rank's broadcast)
 static int prepare_clear_range(const TrainLayout& L, void* ws, int s0, int ns, cudaStream_t st) {
-  const int64_t offs[6] = {L.off_ucnt, L.off_icnt, L.off_iall, L.off_nslow, L.off_nfast, L.off_tcursor};
-  for (int k = 0; k < 6; ++k) APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, offs[k]) + int64_t(s0) * 4, 0, size_t(ns) * 4, st));
+  const int64_t offs[7] = {L.off_ucnt, L.off_icnt, L.off_iall, L.off_nslow, L.off_nfast, L.off_tcursor, L.off_npair};
+  for (int k = 0; k < 7; ++k) APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, offs[k]) + int64_t(s0) * 4, 0, size_t(ns) * 4, st));
   APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_seg_slow) + int64_t(s0) * L.B * 4, 0, size_t(ns) * L.B * 4, st));
+  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_occ_cnt) + int64_t(s0) * L.B * 4, 0, size_t(ns) * L.B * 4, st));
   return APR_OK;
 }
 
@@ -1395,12 +1402,12 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   return APR_OK;
 }
 
-int apr_train_layout(int32_t S, int32_t B, int32_t d, int64_t* out) {
+int apr_train_layout(int32_t S, int32_t B, int32_t d, int64_t* out) {  // 13 entries
   if (!out || S < 1 || B < 1 || !valid_dim(d)) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   out[0] = L.total; out[1] = L.Sc; out[2] = L.off_ucnt; out[3] = L.off_icnt; out[4] = L.off_iall; out[5] = L.off_nslow;
   out[6] = L.off_seg_hdr; out[7] = L.off_rec; out[8] = L.off_iu_item; out[9] = L.off_hdr;
-  out[10] = L.off_npair; out[11] = L.off_nfast;
+  out[10] = L.off_npair; out[11] = L.off_nfast; out[12] = L.off_pairs;
   return APR_OK;
 }
 
@@ -1414,7 +1421,7 @@ int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = clear_counters ? prepare_clear_range(L, ws, s0, ns, st) : APR_OK;
-  for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st, false);
+  for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st, pairs_enabled(d));
   return rc;
 }
 
@@ -1424,7 +1431,7 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
                             int64_t ws_bytes, float* stats, int32_t step, int32_t stage, apr_stream_t stream) {
   if (!Pb || !Qb || !accPb || !accQb || !GQb || !HQb || !ws) return APR_E_ARG;
   if (nranks < 1 || nranks > kMaxRanks || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return APR_E_ARG;
-  if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 3) return APR_E_ARG;
+  if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 4) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   StepCtx c;
@@ -1443,6 +1450,7 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
   c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
   c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt); c.nslow = at<int32_t>(ws, L.off_nslow);
+  c.npair = pairs_enabled(d) ? at<int32_t>(ws, L.off_npair) : nullptr; c.pairs = at<int4>(ws, L.off_pairs);
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr); c.rec = at<int4>(ws, L.off_rec); c.iu_item = at<int32_t>(ws, L.off_iu_item);
   c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf);
   c.stats = stats;
@@ -1516,6 +1524,13 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
       if (r2) return r2;
       APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
       if (timing) cudaEventRecord(ev[7], ax.stream);
+      if (pairs_enabled(d)) {   // pair work units: third stream, no ordering against the other kernels of the step
+        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
+        const int r3 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
+                                               adver, ws, ws_bytes, stats, s, 4, ax.pair_stream);
+        if (r3) return r3;
+        APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
+      }
       return APR_OK;
     };
     if (order == 0 || !adver) { if ((rc = launch_fast())) return rc; }
@@ -1541,6 +1556,7 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
     if (timing) cudaEventRecord(ev[5], st);
     if (order == 2 && adver) { if ((rc = launch_fast())) return rc; }
     APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
+    if (pairs_enabled(d)) APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join2, 0));
     if ((rc = barrier())) return rc;
     if (timing && adver) {
       cudaStreamSynchronize(st);

@@ -173,6 +173,8 @@ def train_steps_sharded(tables: ShardedTables, U: torch.Tensor, I: torch.Tensor,
     views = {
         "ucnt": (L["ucnt"], 4, 1), "icnt": (L["icnt"], 4, 1), "iall": (L["iall"], 4, 1), "nslow": (L["nslow"], 4, 1),
         "seg_hdr": (L["seg_hdr"], 32 * Bg, Bg * 8), "rec": (L["rec"], 16 * Bg, Bg * 4), "iu_item": (L["iu_item"], 4 * Bg, Bg),
+        # pair work units (two single-triple segments coupled by one twice-occurring item; csrc/train.cu pair_unit)
+        "npair": (L["npair"], 4, 1), "pairs": (L["pairs"], 48 * (Bg // 2 + 1), 12 * (Bg // 2 + 1)),
     }
     main = torch.cuda.current_stream()
     for c, s0 in enumerate(range(0, S, L["Sc"])):
@@ -197,9 +199,11 @@ def train_steps_sharded(tables: ShardedTables, U: torch.Tensor, I: torch.Tensor,
                 with torch.cuda.stream(aux_stream):
                     for r in ranks:
                         launch(r, 3)
+                        launch(r, 4)
             else:
                 for r in ranks:
                     launch(r, 3)
+                    launch(r, 4)
             if adver:
                 for r in ranks:
                     launch(r, 0)

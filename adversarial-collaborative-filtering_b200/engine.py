@@ -140,9 +140,9 @@ def train_run(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: Train
 
 def train_layout(n_steps: int, batch: int, d: int) -> dict:
     """Byte offsets of the index arrays inside a TrainWorkspace (for the sharded driver's broadcasts)."""
-    out = (ctypes.c_int64 * 12)()
+    out = (ctypes.c_int64 * 13)()
     _lib.check(_lib.lib().apr_train_layout(n_steps, batch, d, out))
-    keys = ["total", "Sc", "ucnt", "icnt", "iall", "nslow", "seg_hdr", "rec", "iu_item", "hdr", "npair", "nfast"]
+    keys = ["total", "Sc", "ucnt", "icnt", "iall", "nslow", "seg_hdr", "rec", "iu_item", "hdr", "npair", "nfast", "pairs"]
     return dict(zip(keys, [int(v) for v in out]))
 
 

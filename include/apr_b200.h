@@ -106,9 +106,9 @@ int apr_train_unique_counts(const void* workspace, int32_t n_steps, int32_t batc
  *      the shared-item workspace (>= batch/nranks + 1 rows each, zeroed once).  `batch` is the GLOBAL batch; every rank
  *      holds identical index arrays in `workspace` (apr_train_prepare_range on one rank + a broadcast of the regions
  *      apr_train_layout reports) and processes every nranks-th segment.  One call launches ONE stage of ONE step:
- *      stage 0,1,2 = general path, 3 = fast kernel; the caller puts a cross-rank barrier after stages 0, 1 and
- *      after {2,3}.  apr_b200/distributed.py is that caller. */
-int apr_train_layout(int32_t n_steps, int32_t batch, int32_t d, int64_t* out12);
+ *      stage 0,1,2 = general path, 3 = fast kernel, 4 = pair work units; the caller puts a cross-rank barrier after
+ *      stages 0, 1 and after {2,3,4}.  apr_b200/distributed.py is that caller. */
+int apr_train_layout(int32_t n_steps, int32_t batch, int32_t d, int64_t* out13);
 int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch,
                             int32_t d, int64_t rows_p, int64_t rows_q, void* workspace, int64_t workspace_bytes,
                             int32_t first_step, int32_t count, int32_t clear_counters, apr_stream_t stream);
