@@ -203,6 +203,72 @@ __global__ void prep_compact_kernel(int s0, int ns, int B, int Tu, int Ti, const
   }
 }
 
+// Block-aggregated variant for tables that are multiples of 256 entries (batch >= 128): a 256-thread block covers 256
+// consecutive entries of ONE table of ONE step, the eight warps' totals meet in shared memory, and the per-step
+// counters take one atomic per block instead of one per warp -- those same-address atomics were what the kernel cost.
+__global__ void __launch_bounds__(256)
+prep_compact_block_kernel(int s0, int ns, int B, int Tu, int Ti, const int32_t* __restrict__ tkey_u, int32_t* tval_u,
+                          const int32_t* __restrict__ tkey_i, int32_t* tval_i, int32_t* ucnt, int32_t* icnt, int32_t* iall,
+                          int32_t* tcursor, int32_t* seg_user, int32_t* seg_off, int32_t* seg_cnt, int32_t* ucursor,
+                          int32_t* iu_item) {
+  __shared__ int sh_slot[8], sh_tot[8], sh_val[8], sh_base[2];
+  const int64_t nU = int64_t(ns) * Tu, nI = int64_t(ns) * Ti;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = int64_t(blockIdx.x) * 256; base < nU + nI; base += int64_t(gridDim.x) * 256) {
+    const int64_t e = base + threadIdx.x;
+    const bool is_user = base < nU;                 // block-uniform
+    int32_t key, val = 0;
+    int s;
+    int64_t ei = 0;
+    if (is_user) { s = s0 + int(base / Tu); key = tkey_u[e]; if (key != -1) val = tval_u[e]; }
+    else { ei = e - nU; s = s0 + int((base - nU) / Ti); key = tkey_i[ei]; if (key != -1) val = tval_i[ei]; }
+    const bool valid = key != -1;
+    const bool slotted = valid && (is_user || val != 0);
+    const unsigned mv = __ballot_sync(0xffffffffu, valid);
+    const unsigned ms = __ballot_sync(0xffffffffu, slotted);
+    const int cnt = (is_user && valid) ? 1 + val : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (int(lane) >= o) incl += y;
+    }
+    if (lane == 31) { sh_slot[warp] = __popc(ms); sh_tot[warp] = incl; sh_val[warp] = __popc(mv); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int nslot = 0, ntot = 0, nval = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int a = sh_slot[w], b = sh_tot[w];
+        sh_slot[w] = nslot; sh_tot[w] = ntot;       // exclusive prefixes over the warps
+        nslot += a; ntot += b; nval += sh_val[w];
+      }
+      int bslot = 0, boff = 0;
+      if (nval) {
+        if (is_user) { bslot = atomicAdd(&ucnt[s], nslot); boff = atomicAdd(&tcursor[s], ntot); }
+        else { atomicAdd(&iall[s], nval); if (nslot) bslot = atomicAdd(&icnt[s], nslot); }
+      }
+      sh_base[0] = bslot; sh_base[1] = boff;
+    }
+    __syncthreads();
+    if (valid) {
+      const int slot = slotted ? sh_base[0] + sh_slot[warp] + __popc(ms & ((1u << lane) - 1u)) : -1;
+      if (is_user) {
+        const int64_t k = int64_t(s) * B + slot;
+        seg_user[k] = key;
+        seg_off[k] = sh_base[1] + sh_tot[warp] + incl - cnt;
+        seg_cnt[k] = cnt;
+        ucursor[k] = 0;
+        tval_u[e] = slot;
+      } else {
+        if (slot >= 0) iu_item[int64_t(s) * B + slot] = key;
+        tval_i[ei] = slot;
+      }
+    }
+    __syncthreads();   // sh_* are rewritten by the next iteration
+  }
+}
+
 __global__ void prep_scatter_kernel(const int32_t* __restrict__ i, const int32_t* __restrict__ j, int s0, int ns, int B,
                                     int Tu, int Ti, const int32_t* __restrict__ tval_u, const int32_t* __restrict__ tval_i,
                                     const int32_t* __restrict__ entry, const int32_t* __restrict__ seg_off,
@@ -1237,11 +1303,19 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
                                                  tval_i, at<int32_t>(ws, L.off_entry), at<int32_t>(ws, L.off_hdr));
   const int64_t ne = int64_t(ns) * (L.Tu + L.Ti);
   const int grid_b = int(std::max<int64_t>(1, std::min<int64_t>((ne + threads - 1) / threads, cap)));
-  prep_compact_kernel<<<grid_b, threads, 0, st>>>(
-      s0, ns, B, L.Tu, L.Ti, tkey_u, tval_u, tkey_i, tval_i, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_icnt),
-      at<int32_t>(ws, L.off_iall), at<int32_t>(ws, L.off_tcursor), at<int32_t>(ws, L.off_seg_user),
-      at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt), at<int32_t>(ws, L.off_ucursor),
-      at<int32_t>(ws, L.off_iu_item));
+  static const int compact_block = env_int("APR_COMPACT_BLOCK", 1);
+  if (compact_block && L.Tu % 256 == 0 && L.Ti % 256 == 0)
+    prep_compact_block_kernel<<<grid_b, 256, 0, st>>>(
+        s0, ns, B, L.Tu, L.Ti, tkey_u, tval_u, tkey_i, tval_i, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_icnt),
+        at<int32_t>(ws, L.off_iall), at<int32_t>(ws, L.off_tcursor), at<int32_t>(ws, L.off_seg_user),
+        at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt), at<int32_t>(ws, L.off_ucursor),
+        at<int32_t>(ws, L.off_iu_item));
+  else
+    prep_compact_kernel<<<grid_b, threads, 0, st>>>(
+        s0, ns, B, L.Tu, L.Ti, tkey_u, tval_u, tkey_i, tval_i, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_icnt),
+        at<int32_t>(ws, L.off_iall), at<int32_t>(ws, L.off_tcursor), at<int32_t>(ws, L.off_seg_user),
+        at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt), at<int32_t>(ws, L.off_ucursor),
+        at<int32_t>(ws, L.off_iu_item));
   prep_scatter_kernel<<<grid_a, threads, 0, st>>>(i, j, s0, ns, B, L.Tu, L.Ti, tval_u, tval_i, at<int32_t>(ws, L.off_entry),
                                                   at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_ucursor),
                                                   at<int4>(ws, L.off_rec), at<int32_t>(ws, L.off_seg_slow),
