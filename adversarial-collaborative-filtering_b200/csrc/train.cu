@@ -319,7 +319,12 @@ __global__ void prep_pair_kernel(int s0, int ns, int B, const int32_t* __restric
     if (ab.x == ab.y) continue;                                   // i == j inside one triple
     if (seg_cnt[b + ab.x] != 1 || seg_cnt[b + ab.y] != 1) continue;
     if (seg_slow[b + ab.x] != 1 || seg_slow[b + ab.y] != 1) continue;
-    const int k = atomicAdd(&npair[s], 1);
+    // one atomic per (warp, step) instead of one per pair: lanes of the same step allocate together
+    const unsigned peers = __match_any_sync(__activemask(), s);
+    const int leader = __ffs(peers) - 1;
+    int k = 0;
+    if (int(threadIdx.x & 31) == leader) k = atomicAdd(&npair[s], __popc(peers));
+    k = __shfl_sync(peers, k, leader) + __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
     int4* out = pairs + (int64_t(s) * (B / 2 + 1) + k) * 3;
     out[0] = make_int4(seg_user[b + ab.x], seg_user[b + ab.y], slot, 0);
     out[1] = rec[b + seg_off[b + ab.x]];
@@ -379,6 +384,55 @@ __global__ void prep_pack_kernel(int s0, int ns, int B, const int32_t* __restric
       h[0] = make_int4(seg_user[t], b0, b1 - b0, shared);
       h[1] = rec[int64_t(s) * B + b0];
     }
+  }
+}
+
+// Block-aggregated variant for batch % 256 == 0: a block covers 256 segments of ONE step, so the two per-step counters
+// take one atomic per block.
+__global__ void __launch_bounds__(256)
+prep_pack_block_kernel(int s0, int ns, int B, const int32_t* __restrict__ ucnt, const int32_t* __restrict__ seg_user,
+                       const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_cnt,
+                       const int32_t* __restrict__ seg_slow, const int4* __restrict__ rec, int4* seg_hdr, int32_t* nslow,
+                       int32_t* nfast) {
+  __shared__ int sh_s[8], sh_f[8], sh_base[2];
+  const int64_t total = int64_t(ns) * B;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = int64_t(blockIdx.x) * 256; base < total; base += int64_t(gridDim.x) * 256) {
+    const int s = s0 + int(base / B);                       // block-uniform
+    const int seg = int(base - int64_t(s - s0) * B) + threadIdx.x;
+    const int nu = ucnt[s];
+    bool valid = seg < nu;
+    const int64_t t = int64_t(s) * B + seg;
+    const int shared = valid ? seg_slow[t] : 0;
+    if (shared < 0) valid = false;                          // part of a pair
+    int b0 = 0, b1 = 0;
+    if (valid) { b0 = seg_off[t]; b1 = b0 + seg_cnt[t]; }
+    const int slow = (shared || (b1 - b0) != 1) ? 1 : 0;
+    const unsigned m_slow = __ballot_sync(0xffffffffu, valid && slow);
+    const unsigned m_fast = __ballot_sync(0xffffffffu, valid && !slow);
+    if (lane == 0) { sh_s[warp] = __popc(m_slow); sh_f[warp] = __popc(m_fast); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ts = 0, tf = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int a = sh_s[w], b = sh_f[w];
+        sh_s[w] = ts; sh_f[w] = tf;
+        ts += a; tf += b;
+      }
+      sh_base[0] = ts ? atomicAdd(&nslow[s], ts) : 0;
+      sh_base[1] = tf ? atomicAdd(&nfast[s], tf) : 0;
+    }
+    __syncthreads();
+    if (valid) {
+      const unsigned lt = (1u << lane) - 1u;
+      const int k = slow ? sh_base[0] + sh_s[warp] + __popc(m_slow & lt)
+                         : nu - 1 - (sh_base[1] + sh_f[warp] + __popc(m_fast & lt));
+      int4* h = seg_hdr + (int64_t(s) * B + k) * 2;
+      h[0] = make_int4(seg_user[t], b0, b1 - b0, shared);
+      h[1] = rec[int64_t(s) * B + b0];
+    }
+    __syncthreads();
   }
 }
 
@@ -1328,11 +1382,18 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
                                                  at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
                                                  at<int32_t>(ws, L.off_iu_item), at<int32_t>(ws, L.off_npair),
                                                  at<int4>(ws, L.off_pairs));
-  prep_pack_kernel<<<grid_a, threads, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_seg_user),
-                                               at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
-                                               at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
-                                               at<int4>(ws, L.off_seg_hdr), at<int32_t>(ws, L.off_nslow),
-                                               at<int32_t>(ws, L.off_nfast));
+  if (compact_block && B % 256 == 0)
+    prep_pack_block_kernel<<<grid_a, 256, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_seg_user),
+                                                   at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
+                                                   at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
+                                                   at<int4>(ws, L.off_seg_hdr), at<int32_t>(ws, L.off_nslow),
+                                                   at<int32_t>(ws, L.off_nfast));
+  else
+    prep_pack_kernel<<<grid_a, threads, 0, st>>>(s0, ns, B, at<int32_t>(ws, L.off_ucnt), at<int32_t>(ws, L.off_seg_user),
+                                                 at<int32_t>(ws, L.off_seg_off), at<int32_t>(ws, L.off_seg_cnt),
+                                                 at<int32_t>(ws, L.off_seg_slow), at<int4>(ws, L.off_rec),
+                                                 at<int4>(ws, L.off_seg_hdr), at<int32_t>(ws, L.off_nslow),
+                                                 at<int32_t>(ws, L.off_nfast));
   APR_LAUNCH_CHECK();
   return APR_OK;
 }
