@@ -112,13 +112,13 @@ static bool pairs_enabled(int d) {
 // prepare kernels (all steps of a sub-chunk in parallel; one hash table per step).  `s0` = first step of the
 // sub-chunk: per-step arrays are indexed by the absolute step, tables by the step within the sub-chunk.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t hash_insert(int32_t* table, int T, int32_t key, bool& dup) {
-  uint32_t h = fmix32(uint32_t(key)) & uint32_t(T - 1);
+// continue an insertion whose first probe (slot h) returned `prev`
+__device__ __forceinline__ uint32_t hash_resolve(int32_t* table, int T, int32_t key, uint32_t h, int32_t prev, bool& dup) {
   while (true) {
-    const int32_t prev = atomicCAS(&table[h], -1, key);
     if (prev == -1) { dup = false; return h; }
     if (prev == key) { dup = true; return h; }
     h = (h + 1) & uint32_t(T - 1);
+    prev = atomicCAS(&table[h], -1, key);
   }
 }
 
@@ -135,12 +135,22 @@ __global__ void prep_insert_kernel(const int32_t* __restrict__ u, const int32_t*
     if (ku < 0 || ku >= rows_p) { atomicOr(hdr, 1); ku = 0; }
     if (ki < 0 || ki >= rows_q) { atomicOr(hdr, 1); ki = 0; }
     if (kj < 0 || kj >= rows_q) { atomicOr(hdr, 1); kj = 0; }
+    // the three first probes go out together (independent L2 atomics in flight), collisions are resolved afterwards;
+    // i and j share a table: the two CAS of one thread to one address stay in program order, so i == j makes j a duplicate
+    int32_t* tu = tkey_u + int64_t(sl) * Tu;
+    int32_t* ti = tkey_i + int64_t(sl) * Ti;
+    uint32_t hu = fmix32(uint32_t(ku)) & uint32_t(Tu - 1);
+    uint32_t hi = fmix32(uint32_t(ki)) & uint32_t(Ti - 1);
+    uint32_t hj = fmix32(uint32_t(kj)) & uint32_t(Ti - 1);
+    const int32_t pu = atomicCAS(&tu[hu], -1, ku);
+    const int32_t pi = atomicCAS(&ti[hi], -1, ki);
+    const int32_t pj = atomicCAS(&ti[hj], -1, kj);
     bool dup;
-    const uint32_t hu = hash_insert(tkey_u + int64_t(sl) * Tu, Tu, ku, dup);
+    hu = hash_resolve(tu, Tu, ku, hu, pu, dup);
     if (dup) atomicAdd(&tval_u[int64_t(sl) * Tu + hu], 1);
-    const uint32_t hi = hash_insert(tkey_i + int64_t(sl) * Ti, Ti, ki, dup);
+    hi = hash_resolve(ti, Ti, ki, hi, pi, dup);
     if (dup) tval_i[int64_t(sl) * Ti + hi] = 1;
-    const uint32_t hj = hash_insert(tkey_i + int64_t(sl) * Ti, Ti, kj, dup);
+    hj = hash_resolve(ti, Ti, kj, hj, pj, dup);
     if (dup) tval_i[int64_t(sl) * Ti + hj] = 1;
     entry[3 * t] = int32_t(hu); entry[3 * t + 1] = int32_t(hi); entry[3 * t + 2] = int32_t(hj);
   }
