@@ -11,20 +11,29 @@
 //             sort) owned by one lane group, so user-side sums (G_P, g_P) live in registers.
 //             Items: an item that occurs ONCE in the batch is a singleton -- its row sums are local to its triple.
 //             Only SHARED items (>= 2 occurrences) get a slot in the L2-resident workspace G_Q / H_Q [<= B, d].
-//             Segments are PARTITIONED: slow ones (touching a shared item) first, fast ones after.
-//   FAST segment (no shared item; ~94% at B=65536 on 10M x 2M): the whole APR step in registers -- gather p, q, n
-//             and the three Adagrad rows with 128-bit loads, x, c = -sigma(-x), Delta from the local gradients,
-//             adversarial forward, total gradient, Adagrad, six row stores.  HBM traffic is exactly the algorithmic
-//             4 row-transfers per touched row; nothing else is written.
-//   SLOW segments, three stages separated by grid-wide ordering:
+//             Segments are PARTITIONED: general ones (touching a shared item, or several triples of one user) first,
+//             fast ones at the end; in between, the segments taken by PAIR work units (below).
+//   FAST segment (one triple, no shared item; ~88% at B=65536 on 10M x 2M): the whole APR step in registers -- gather
+//             p, q, n and the three Adagrad rows with 128-bit loads, x, c = -sigma(-x), Delta from the local gradients,
+//             adversarial forward (closed form), total gradient, Adagrad, six row stores.  HBM traffic is exactly the
+//             algorithmic 4 row-transfers per touched row; nothing else is written.
+//   PAIR work unit (~10% of the segments): two single-triple segments whose only coupling to the rest of the batch is
+//             one item that occurs in both and nowhere else -- both triples in registers, the shared item's gradient
+//             sums are two-term sums (pair_unit).  No workspace, no RED, no stage split.
+//   GENERAL segments (the remaining ~2%), three stages separated by grid-wide ordering:
 //     stage 0  plain forward: G_P kept, c kept per triple, G_Q[slot] += +-c p by 16-byte vector RED at L2.
 //     stage 1  Delta_P from G_P, Delta_Q from G_Q[slot] (shared) or c p (singleton), adversarial forward; user row and
-//              singleton item rows get Adagrad directly; H_Q[slot] += g (RED).   + first half of the fast segments
-//     stage 2  per shared slot: Adagrad on the item row from H_Q[slot]; slots re-zeroed.  + second half of the fast ones
-//   so the slow path's dependent-load chains run under the fast bulk.  BPR (adver=0) has no stage 0.
-//   Delta and per-triple gradients never exist in HBM as tables.
-//   mode 0 launches one kernel per stage; mode 1 runs all steps in ONE persistent cooperative kernel with grid
-//   barriers between stages (one barrier per step when the batch has no shared item).
+//              singleton item rows get Adagrad directly; H_Q[slot] += g (RED).
+//     stage 2  per shared slot: Adagrad on the item row from H_Q[slot]; slots re-zeroed.
+//   BPR (adver=0) has no stage 0.  Delta and per-triple gradients never exist in HBM as tables.
+//   mode 0: per step one fast kernel (second stream), one pair kernel (third stream) and one kernel per general stage
+//           (caller's stream), forked from / joined to the caller's stream; index preparation runs one L2-sized
+//           sub-chunk ahead on a fourth, low-priority stream.
+//   mode 1: all steps in ONE persistent cooperative kernel with grid barriers between stages.
+//   mode 2: the same persistent kernel launched as ONE thread-block cluster (<= 16 CTAs, cluster barriers): batches of
+//           a few hundred triples whose steps take a few microseconds.
+//   Row-sharded tables (nranks > 1): every row access goes through shard_row(); a segment / pair is processed by the
+//   rank that owns its (first) user row; apr_train_steps_sharded adds the cross-rank barriers.
 #include <cooperative_groups.h>
 
 #include <algorithm>
