@@ -1166,8 +1166,14 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
   }
 }
 
+struct GraphSlot { cudaGraphExec_t exec = nullptr; cudaEvent_t done = nullptr; };
+
 // second stream + events for the fork/join of mode 0 (created once per process; no device memory)
 struct AuxStream {
+  static constexpr int kGraphSlots = 4;
+  GraphSlot graph_slots[kGraphSlots];
+  int graph_next = 0;
+  cudaStream_t capture_stream = nullptr;  // APR_GRAPH: origin stream of the stream capture
   cudaStream_t stream = nullptr;       // fast-path kernels of mode 0
   cudaStream_t pair_stream = nullptr;  // pair work units of mode 0
   cudaEvent_t join2 = nullptr;
@@ -1194,6 +1200,7 @@ static AuxStream& aux_stream() {
     if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
         cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
         cudaStreamCreateWithPriority(&a.pair_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+        cudaStreamCreateWithFlags(&a.capture_stream, cudaStreamNonBlocking) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
         cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
@@ -1236,24 +1243,65 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
     }
     const bool pairs = V == 1 && c.npair != nullptr;
     const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
-    for (int s = c.s_begin; s < c.s_end; ++s) {
-      APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
-      APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
-      fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.stream>>>(c, s);
-      APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
-      if (pairs) {
-        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
-        if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(c, s);
-        APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
+    auto issue = [&](cudaStream_t main) -> int {
+      for (int s = c.s_begin; s < c.s_end; ++s) {
+        APR_CUDA_CHECK(cudaEventRecord(ax.fork, main));
+        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
+        fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.stream>>>(c, s);
+        APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+        if (pairs) {
+          APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
+          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(c, s);
+          APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
+        }
+        if (c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 0);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 1);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 2);
+        APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join, 0));
+        if (pairs) APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join2, 0));
       }
-      if (c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 0);
-      general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 1);
-      general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 2);
-      APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join, 0));
-      if (pairs) APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.join2, 0));
+      APR_LAUNCH_CHECK();
+      return APR_OK;
+    };
+    // CUDA-graph replay: the launches of this call are captured into ONE CUDA graph (kernel nodes + the fork/join edges of the
+    // three streams) and replayed on the caller's stream, so the dependent launches of a step cost graph-edge latency
+    // instead of stream/event latency.  Instantiating a graph per call costs the host more than it saves, so a small
+    // ring of executable graphs is kept and UPDATED in place from each new capture (same topology: only kernel
+    // parameters change); a different topology (other step count, BPR vs APR) re-instantiates that slot.
+    // Capturing costs the host about what launching does, plus the update: only worth it when a step is long enough
+    // for the host to stay ahead (batches of tens of thousands of triples); APR_GRAPH=0 switches it off.
+    static const int use_graph = env_int("APR_GRAPH", 1), graph_min_batch = env_int("APR_GRAPH_MIN_BATCH", 32768);
+    if (use_graph && c.B >= graph_min_batch && c.s_end - c.s_begin >= 2 && ax.capture_stream) {
+      APR_CUDA_CHECK(cudaStreamBeginCapture(ax.capture_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = issue(ax.capture_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ee = cudaStreamEndCapture(ax.capture_stream, &graph);
+      if (rc != APR_OK || ee != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (ee != cudaSuccess) { set_cuda_error(ee, "cudaStreamEndCapture"); return APR_E_CUDA; }
+        return rc != APR_OK ? rc : APR_E_CUDA;
+      }
+      GraphSlot& sl = ax.graph_slots[ax.graph_next];
+      ax.graph_next = (ax.graph_next + 1) % AuxStream::kGraphSlots;
+      cudaError_t e2 = cudaSuccess;
+      if (!sl.done) e2 = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+      else e2 = cudaEventSynchronize(sl.done);            // the previous launch of this executable graph has finished
+      if (e2 == cudaSuccess && sl.exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(sl.exec, graph, &info) != cudaSuccess) {
+          cudaGetLastError();                             // topology changed: rebuild this slot
+          cudaGraphExecDestroy(sl.exec);
+          sl.exec = nullptr;
+        }
+      }
+      if (e2 == cudaSuccess && !sl.exec) e2 = cudaGraphInstantiate(&sl.exec, graph, 0);
+      if (e2 == cudaSuccess) e2 = cudaGraphLaunch(sl.exec, st);
+      if (e2 == cudaSuccess) e2 = cudaEventRecord(sl.done, st);
+      cudaGraphDestroy(graph);
+      if (e2 != cudaSuccess) { set_cuda_error(e2, "CUDA graph replay"); return APR_E_CUDA; }
+      return APR_OK;
     }
-    APR_LAUNCH_CHECK();
-    return APR_OK;
+    return issue(st);
   }
   if (mode == 2) {
     // small batches (tables in L2, steps of a few microseconds): ONE cluster of up to 16 CTAs runs every step of the
@@ -1514,7 +1562,13 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
-  return run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, 0, S, st);
+  // same sub-chunk granularity as apr_train_steps (mode 0: the same launch sequences, hence the same CUDA graphs)
+  const int sub = mode == 0 ? L.Sc : S;
+  for (int s0 = 0; s0 < S; s0 += sub) {
+    rc = run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, s0, std::min(S, s0 + sub), st);
+    if (rc) return rc;
+  }
+  return APR_OK;
 }
 
 // prepare + run, software-pipelined: the index preparation of sub-chunk c+1 runs on its own stream while the step

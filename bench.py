@@ -422,6 +422,9 @@ def main_single(args):
         engine.train_prepare(P, Q, *c, ws)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the prepared chunk runs twice back to back and the SECOND run is timed: its launches are enqueued while the
+        # first run executes, so the events bracket device time only (not the host's enqueue / graph-update time)
+        engine.train_run(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
         e0.record()
         engine.train_run(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
         e1.record()
