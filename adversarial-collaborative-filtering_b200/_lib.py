@@ -42,17 +42,35 @@ def needs_build() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc-compile every CUDA source for sm_100a into the in-tree shared library."""
+    """nvcc-compile every CUDA source for sm_100a into the in-tree shared library (one object per source, compiled in
+    parallel; an object is rebuilt when its source or any header is newer)."""
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    hdrs = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(REPO_DIR, "include", "apr_b200.h"))
+    t_hdr = max(os.path.getmtime(h) for h in hdrs)
+    jobs, objs = [], []
+    for src in _sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(t_hdr, os.path.getmtime(src)):
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for cmd, proc in jobs:
+        _, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), err[-4000:]))
+        if verbose:
+            print(err)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
     return LIB_PATH
 
 
@@ -63,6 +81,9 @@ _SIGNATURES = {
     "apr_status_string": (c_char_p, [ctypes.c_int]),
     "apr_last_cuda_error": (c_char_p, []),
     "apr_device_info": (ctypes.c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "apr_context_create": (ctypes.c_int, [c_int32]),
+    "apr_context_destroy": (ctypes.c_int, [c_int32]),
+    "apr_context_stats": (ctypes.c_int, [POINTER(c_int64)]),
     "apr_init_truncated_normal": (ctypes.c_int, [_P, c_int64, c_int32, c_float, c_uint32, c_uint32, c_uint32, _P]),
     "apr_fill_f32": (ctypes.c_int, [_P, c_int64, c_float, _P]),
     "apr_sample_epoch": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_uint32, c_uint32, c_int32,

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "context.cuh"
 
 namespace apr {
 
@@ -551,27 +552,26 @@ int launch_excl_correction(const float* P, const float* Q, int d, const int32_t*
 
 using namespace apr;
 
-// optional phase timing (apr_eval_tc_timing): events around the GEMM kernel of the most recent apr_eval_fullrank_tc call
-static bool g_tc_timing = false;
-static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
-static bool g_tc_ev_valid = false;
-
 extern "C" {
 
+// optional phase timing: events (per-device context) around the GEMM kernel of the most recent apr_eval_fullrank_tc call
 int apr_eval_tc_timing(int32_t enable, float* gemm_ms_out) {
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   if (gemm_ms_out) {
     *gemm_ms_out = -1.f;
-    if (g_tc_ev_valid) {
-      APR_CUDA_CHECK(cudaEventSynchronize(g_tc_ev[1]));
-      APR_CUDA_CHECK(cudaEventElapsedTime(gemm_ms_out, g_tc_ev[0], g_tc_ev[1]));
+    if (ctx->tc_ev_valid) {
+      APR_CUDA_CHECK(cudaEventSynchronize(ctx->tc_ev[1]));
+      APR_CUDA_CHECK(cudaEventElapsedTime(gemm_ms_out, ctx->tc_ev[0], ctx->tc_ev[1]));
     }
   }
-  if (enable && !g_tc_ev[0]) {
-    APR_CUDA_CHECK(cudaEventCreate(&g_tc_ev[0]));
-    APR_CUDA_CHECK(cudaEventCreate(&g_tc_ev[1]));
+  if (enable && !ctx->tc_ev[0]) {
+    APR_CUDA_CHECK(cudaEventCreate(&ctx->tc_ev[0]));
+    APR_CUDA_CHECK(cudaEventCreate(&ctx->tc_ev[1]));
   }
-  g_tc_timing = enable != 0;
-  if (!g_tc_timing) g_tc_ev_valid = false;
+  ctx->tc_timing = enable != 0;
+  if (!ctx->tc_timing) ctx->tc_ev_valid = false;
   return APR_OK;
 }
 
@@ -593,6 +593,9 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   const TcWs W = tc_ws(n_users, n_items, d);
   if (ws_bytes < W.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   char* base = static_cast<char*>(ws);
   float* spos = reinterpret_cast<float*>(base + W.off_spos);
   float* uscale = reinterpret_cast<float*>(base + W.off_scale);
@@ -657,7 +660,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   if (cap_cta < 16) return APR_E_UNSUPPORTED;
   const int32_t meta[2] = {n_ctas, cap_cta};
   APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
-  if (g_tc_timing) APR_CUDA_CHECK(cudaEventRecord(g_tc_ev[0], st));
+  if (ctx->tc_timing) APR_CUDA_CHECK(cudaEventRecord(ctx->tc_ev[0], st));
   {
     cudaError_t attr_err = cudaSuccess;
     auto launch = [&](auto kern) {
@@ -673,7 +676,7 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
     else launch(tc_count_kernel<0, 0>);
     APR_CUDA_CHECK(attr_err);
   }
-  if (g_tc_timing) { APR_CUDA_CHECK(cudaEventRecord(g_tc_ev[1], st)); g_tc_ev_valid = true; }
+  if (ctx->tc_timing) { APR_CUDA_CHECK(cudaEventRecord(ctx->tc_ev[1], st)); ctx->tc_ev_valid = true; }
   APR_LAUNCH_CHECK();
   {  // d % 8 == 0 here (checked on entry), so rows are whole float4 pieces
     const int gx = std::max(1, std::min(8, (sms * 6) / std::max(1, n_ctas)));

@@ -43,6 +43,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "context.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -459,6 +460,11 @@ prep_pack_block_kernel(int s0, int ns, int B, const int32_t* __restrict__ ucnt, 
 // step kernels
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxRanks = 8;
+// The per-launch part of a step's arguments, kept in DEVICE memory (workspace header, byte 64) so that an executable CUDA
+// graph of the step can be replayed without touching its kernel parameters: `s` = absolute step the next graph launch
+// starts at (advanced by the graph's last node), `stats` = the caller's per-step {loss, correct} array (nullable).
+struct StepDyn { int s; int pad; float* stats; };
+constexpr int64_t kDynOffset = 64;
 // Tables are row-sharded: row r lives on rank r & (nranks-1) at local row r >> rshift (nranks a power of two; 1 on a
 // single GPU).  Pb/Qb/... hold every rank's shard base (peer-mapped over NVLink); G_Q/H_Q slots are sharded the same way.
 struct StepCtx {
@@ -474,6 +480,7 @@ struct StepCtx {
   const int4* seg_hdr; const int4* rec; const int32_t* iu_item;
   float* GP; float* cbuf;
   float* stats;  // nullable [S,2]
+  const StepDyn* dyn;   // non-null inside a replayed CUDA graph: step = dyn->s + the kernel's step parameter, stats = dyn->stats
   int flags;     // tuning switches (APR_STEP_FLAGS)
   int s_begin, s_end;  // steps of this launch
   int only_stage;      // -1: whole step; 0,1,2: that general stage; 3: fast kernel (sharded driver, one launch per call)
@@ -648,7 +655,7 @@ __device__ __forceinline__ void adv_triple(const StepCtx& c, const int4 rc, floa
   item_sink<G, V>(c, rc.y, rc.w, n, hj, lane, d);
 }
 
-struct StepStats { float loss, correct; };
+struct StepStats { float loss, correct; bool on; };
 
 template <int G>
 __device__ __forceinline__ int4 shfl4(unsigned mask, const int4 v, int src) {
@@ -709,7 +716,7 @@ __device__ __forceinline__ void fast_segment(const StepCtx& c, const int user, c
   const float x = s_pq - s_pn;
   float r;
   const float cf = bpr_coeff(x, r);
-  if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+  if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
   float A = cf, Bc = c.kreg, Cc = 0.f;
   if (c.adver) {
     const float a = c.eps * cf * rsqrt_fast(fmaxf(cf * cf * s_dd, 1e-12f));
@@ -809,7 +816,7 @@ __device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0
     const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
     float r;
     const float cf = bpr_coeff(x, r);
-    if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+    if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
 #pragma unroll
     for (int k = 0; k < V; ++k) g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]);
     if (!adver) {
@@ -863,7 +870,7 @@ __device__ __forceinline__ void slow_plain(const StepCtx& c, int k0, const int4 
     const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
     float r;
     const float cf = bpr_coeff(x, r);
-    if (c.stats) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+    if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
     Row<G, V> t;
 #pragma unroll
     for (int k = 0; k < V; ++k) { g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]); t.v[k] = f4_scale(p.v[k], cf); }
@@ -960,7 +967,7 @@ __device__ __forceinline__ void pair_unit(const StepCtx& c, const int4 ph, const
   const float xb = row_dot<G, V>(pb, qb, mask) - row_dot<G, V>(pb, nb, mask);
   float r0, r1;
   const float ca = bpr_coeff(xa, r0), cb = bpr_coeff(xb, r1);
-  if (c.stats) {
+  if (st.on) {
     st.loss += softplus_neg(r0) + softplus_neg(r1);
     st.correct += ((xa > 0.f) ? 1.f : 0.f) + ((xb > 0.f) ? 1.f : 0.f);
   }
@@ -1100,38 +1107,50 @@ __device__ __forceinline__ unsigned group_mask() {
 }
 
 // mode 0: general-path stage kernel (small grid) ...
+// step / stats of a mode-0 kernel: straight from the parameters, or relative to the device-side cursor when the launch
+// is a node of a replayed CUDA graph
+#define APR_STEP_ARGS(c, s_param)                                   \
+  const int s = (c).dyn ? (c).dyn->s + (s_param) : (s_param);       \
+  float* const stats = (c).dyn ? (c).dyn->stats : (c).stats;        \
+  StepStats st = {0.f, 0.f, stats != nullptr};
+
 template <int G, int V>
-__global__ void __launch_bounds__(kThreads) general_stage_kernel(StepCtx c, int s, int stage) {
+__global__ void __launch_bounds__(kThreads) general_stage_kernel(StepCtx c, int s_param, int stage) {
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
-  StepStats st = {0.f, 0.f};
+  APR_STEP_ARGS(c, s_param)
   if (stage == 0 && !(c.adver && c.icnt[s] > 0)) return;
   general_stage<G, V>(c, s, stage, gid, ngroups, lane, group_mask<G>(), st);
-  if (c.stats && stage < 2) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+  if (stats && stage < 2) stats_flush(stats, s, st.loss, st.correct, lane == 0);
 }
 
 // ... and the fast-path kernel, launched on a second stream so that the general path's load chains hide under it
 template <int G, int V, bool FULL>
-__global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fast_kernel(StepCtx c, int s) {
+__global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fast_kernel(StepCtx c, int s_param) {
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
-  StepStats st = {0.f, 0.f};
+  APR_STEP_ARGS(c, s_param)
   fast_range<G, V, FULL>(c, s, c.nslow[s] + (c.npair ? 2 * c.npair[s] : 0), c.ucnt[s], gid, ngroups, lane, group_mask<G>(), st);
-  if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+  if (stats) stats_flush(stats, s, st.loss, st.correct, lane == 0);
 }
 
 // mode 0: the pair work units of one step (third stream; touches rows no other kernel of the step touches)
 template <int G, int V>
-__global__ void __launch_bounds__(kThreads, 2) pair_kernel(StepCtx c, int s) {
+__global__ void __launch_bounds__(kThreads, 2) pair_kernel(StepCtx c, int s_param) {
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
-  StepStats st = {0.f, 0.f};
+  APR_STEP_ARGS(c, s_param)
   pair_range<G, V>(c, s, gid, ngroups, lane, group_mask<G>(), st);
-  if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+  if (stats) stats_flush(stats, s, st.loss, st.correct, lane == 0);
 }
+
+// device-side step cursor of the replayed graphs (StepDyn): set before the first graph launch of a call, advanced by the
+// last node of every graph
+__global__ void dyn_set_kernel(StepDyn* dyn, int s, float* stats) { dyn->s = s; dyn->stats = stats; }
+__global__ void dyn_advance_kernel(StepDyn* dyn, int n) { dyn->s += n; }
 
 // mode 1: all steps in one cooperative launch; the general stages run under the two halves of the fast range
 template <int G, int V, bool FULL>
@@ -1148,7 +1167,7 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
     const int nu = c.ucnt[s], ng = c.nslow[s] + (c.npair ? 2 * c.npair[s] : 0);   // ng: first fast segment
     const bool shared = c.icnt[s] > 0;  // grid-uniform
     const int mid = ng + (nu - ng + 1) / 2;
-    StepStats st = {0.f, 0.f};
+    StepStats st = {0.f, 0.f, c.stats != nullptr};
     if (shared && c.adver) {
       general_stage<G, V>(c, s, 0, gid, ngroups, lane, mask, st);
       sync_all();
@@ -1166,61 +1185,89 @@ __global__ void __launch_bounds__(kThreads) step_persistent_kernel(StepCtx c) {
   }
 }
 
-struct GraphSlot { cudaGraphExec_t exec = nullptr; cudaEvent_t done = nullptr; };
-
-// second stream + events for the fork/join of mode 0 (created once per process; no device memory)
-struct AuxStream {
-  static constexpr int kGraphSlots = 4;
-  GraphSlot graph_slots[kGraphSlots];
-  int graph_next = 0;
-  cudaStream_t capture_stream = nullptr;  // APR_GRAPH: origin stream of the stream capture
-  cudaStream_t stream = nullptr;       // fast-path kernels of mode 0
-  cudaStream_t pair_stream = nullptr;  // pair work units of mode 0
-  cudaEvent_t join2 = nullptr;
-  cudaStream_t prep_stream = nullptr;  // index preparation, pipelined one sub-chunk ahead of the step kernels
-  cudaEvent_t fork = nullptr, join = nullptr, entry = nullptr;
-  std::vector<cudaEvent_t> prep_done;
-  bool ok = false;
-  cudaEvent_t prep_event(size_t k) {
-    while (prep_done.size() <= k) {
-      cudaEvent_t e = nullptr;
-      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-      prep_done.push_back(e);
-    }
-    return prep_done[k];
-  }
-};
-static AuxStream& aux_stream() {
-  static AuxStream a;
-  if (!a.ok) {
-    // index preparation runs at the LOWEST priority (it only has to stay one sub-chunk ahead: let it fill the gaps the
-    // step kernels leave), the fast-path kernels at the highest
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-        cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-        cudaStreamCreateWithPriority(&a.pair_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-        cudaStreamCreateWithFlags(&a.capture_stream, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming) == cudaSuccess)
-      a.ok = true;
-  }
-  return a;
-}
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph replay of mode 0.  The launches of a GROUP of n steps (n in kGraphGroups: per step the fast kernel, the pair
+// kernel, the general stages and the fork/join edges of the three streams, then one node that advances the device-side
+// step cursor) are captured ONCE into an executable graph whose kernel parameters do not depend on which steps it runs:
+// the step index is `dyn->s + k` with dyn in the workspace header.  Executable graphs are cached per device, keyed by
+// the bytes of the static StepCtx (tables, workspace, hyper-parameters, batch, d) + kernel instantiation + n; when a key
+// is seen for the first time ALL group sizes are built, so no cudaGraphInstantiate can happen later for any step count
+// of that configuration (round 1 keyed a 4-slot ring by the call's step count: a 20-step call after a 5-step warm-up
+// re-instantiated inside the timed region).  A full cache recycles its least recently used graph of the same topology
+// through cudaGraphExecUpdate (parameters only).
+// ------------------------------------------------------------------------------------------------
+constexpr int kGraphGroups[] = {8, 4, 2, 1};
+constexpr size_t kGraphCacheMax = 64;
+
+static GraphEntry* graph_find(DeviceContext& ax, const StepCtx& key, const void* fn, int n) {
+  for (auto& g : ax.graphs)
+    if (g.exec && g.fn == fn && g.n_steps == n && g.key.size() == sizeof(StepCtx) && memcmp(g.key.data(), &key, sizeof(StepCtx)) == 0)
+      return &g;
+  return nullptr;
+}
+
+// capture `issue(capture_stream, n)` and turn it into the executable graph of (key, fn, n)
+template <typename Issue>
+static int graph_build(DeviceContext& ax, const StepCtx& key, const void* fn, int n, int topo, Issue&& issue, GraphEntry** out) {
+  APR_CUDA_CHECK(cudaStreamBeginCapture(ax.capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = issue(ax.capture_stream, n);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ee = cudaStreamEndCapture(ax.capture_stream, &graph);
+  if (rc != APR_OK || ee != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (ee != cudaSuccess) { set_cuda_error(ee, "cudaStreamEndCapture"); return APR_E_CUDA; }
+    return rc != APR_OK ? rc : APR_E_CUDA;
+  }
+  GraphEntry* e = nullptr;
+  if (ax.graphs.size() >= kGraphCacheMax) {
+    // recycle: least recently used entry, preferring one whose topology matches (update in place, no instantiate)
+    for (int pass = 0; pass < 2 && !e; ++pass)
+      for (auto& g : ax.graphs)
+        if ((pass == 1 || (g.fn == fn && g.n_steps == n && g.topo == topo)) && (!e || g.last_use < e->last_use)) e = &g;
+  } else {
+    ax.graphs.reserve(kGraphCacheMax);   // entries are handed out by pointer: never reallocate
+    ax.graphs.emplace_back();
+    e = &ax.graphs.back();
+  }
+  cudaError_t e2 = cudaSuccess;
+  if (!e->done) e2 = cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming);
+  else e2 = cudaEventSynchronize(e->done);   // its last launch has finished
+  if (e2 == cudaSuccess && e->exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (e->fn == fn && e->n_steps == n && e->topo == topo && cudaGraphExecUpdate(e->exec, graph, &info) == cudaSuccess) {
+      ++ax.graph_updates;
+    } else {
+      cudaGetLastError();
+      cudaGraphExecDestroy(e->exec);
+      e->exec = nullptr;
+    }
+  }
+  if (e2 == cudaSuccess && !e->exec) {
+    e2 = cudaGraphInstantiate(&e->exec, graph, 0);
+    ++ax.graph_instantiations;
+  }
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) { e->exec = nullptr; e->key.clear(); set_cuda_error(e2, "CUDA graph build"); return APR_E_CUDA; }
+  e->key.assign(reinterpret_cast<const unsigned char*>(&key), reinterpret_cast<const unsigned char*>(&key) + sizeof(StepCtx));
+  e->fn = fn; e->n_steps = n; e->topo = topo;
+  e->last_use = ++ax.graph_clock;
+  *out = e;
+  return APR_OK;
+}
+
 template <int G, int V, bool FULL>
-static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
+static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDyn* dyn_dev) {
   const int gpb = kThreads / G;
   const int sms = sm_count();
   if (mode == 0) {
-    AuxStream& ax = aux_stream();
-    if (!ax.ok) return APR_E_CUDA;
+    DeviceContext* axp = device_context();
+    if (!axp) return APR_E_CUDA;
+    DeviceContext& ax = *axp;
     int occ_fast = 0;
     APR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, fast_kernel<G, V, FULL>, kThreads, 0));
     // resident blocks per SM are shared between the fast kernel and the general-path kernels running next to it
@@ -1243,65 +1290,69 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
     }
     const bool pairs = V == 1 && c.npair != nullptr;
     const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
-    auto issue = [&](cudaStream_t main) -> int {
-      for (int s = c.s_begin; s < c.s_end; ++s) {
+    // the launches of steps [s0, s1) with context cc, forked from / joined to `main`
+    auto issue_steps = [&](const StepCtx& cc, cudaStream_t main, int s0, int s1) -> int {
+      for (int s = s0; s < s1; ++s) {
         APR_CUDA_CHECK(cudaEventRecord(ax.fork, main));
-        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
-        fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.stream>>>(c, s);
-        APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
+        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.fast_stream, ax.fork, 0));
+        fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.fast_stream>>>(cc, s);
+        APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.fast_stream));
         if (pairs) {
           APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
-          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(c, s);
+          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(cc, s);
           APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
         }
-        if (c.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 0);
-        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 1);
-        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(c, s, 2);
+        if (cc.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 0);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 1);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 2);
         APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join, 0));
         if (pairs) APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join2, 0));
       }
       APR_LAUNCH_CHECK();
       return APR_OK;
     };
-    // CUDA-graph replay: the launches of this call are captured into ONE CUDA graph (kernel nodes + the fork/join edges of the
-    // three streams) and replayed on the caller's stream, so the dependent launches of a step cost graph-edge latency
-    // instead of stream/event latency.  Instantiating a graph per call costs the host more than it saves, so a small
-    // ring of executable graphs is kept and UPDATED in place from each new capture (same topology: only kernel
-    // parameters change); a different topology (other step count, BPR vs APR) re-instantiates that slot.
-    // Capturing costs the host about what launching does, plus the update: only worth it when a step is long enough
-    // for the host to stay ahead (batches of tens of thousands of triples); APR_GRAPH=0 switches it off.
+    // Graph replay pays off when a step is long enough for the saved dependency latency to matter and the batch is large
+    // enough for the three-stream layout (APR_GRAPH=0 switches it off, APR_GRAPH_MIN_BATCH moves the threshold).
     static const int use_graph = env_int("APR_GRAPH", 1), graph_min_batch = env_int("APR_GRAPH_MIN_BATCH", 32768);
-    if (use_graph && c.B >= graph_min_batch && c.s_end - c.s_begin >= 2 && ax.capture_stream) {
-      APR_CUDA_CHECK(cudaStreamBeginCapture(ax.capture_stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = issue(ax.capture_stream);
-      cudaGraph_t graph = nullptr;
-      const cudaError_t ee = cudaStreamEndCapture(ax.capture_stream, &graph);
-      if (rc != APR_OK || ee != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        if (ee != cudaSuccess) { set_cuda_error(ee, "cudaStreamEndCapture"); return APR_E_CUDA; }
-        return rc != APR_OK ? rc : APR_E_CUDA;
-      }
-      GraphSlot& sl = ax.graph_slots[ax.graph_next];
-      ax.graph_next = (ax.graph_next + 1) % AuxStream::kGraphSlots;
-      cudaError_t e2 = cudaSuccess;
-      if (!sl.done) e2 = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
-      else e2 = cudaEventSynchronize(sl.done);            // the previous launch of this executable graph has finished
-      if (e2 == cudaSuccess && sl.exec) {
-        cudaGraphExecUpdateResultInfo info;
-        if (cudaGraphExecUpdate(sl.exec, graph, &info) != cudaSuccess) {
-          cudaGetLastError();                             // topology changed: rebuild this slot
-          cudaGraphExecDestroy(sl.exec);
-          sl.exec = nullptr;
+    if (use_graph && c.B >= graph_min_batch && dyn_dev) {
+      StepCtx key = c;                    // static part: everything except the steps and the stats pointer of this call
+      key.s_begin = key.s_end = 0;
+      key.stats = nullptr;
+      key.dyn = dyn_dev;
+      const void* fn = reinterpret_cast<const void*>(&fast_kernel<G, V, FULL>);
+      const int topo = (c.adver ? 1 : 0) | (pairs ? 2 : 0);
+      auto issue_group = [&](cudaStream_t main, int n) -> int {
+        const int rc = issue_steps(key, main, 0, n);
+        if (rc) return rc;
+        dyn_advance_kernel<<<1, 1, 0, main>>>(const_cast<StepDyn*>(dyn_dev), n);
+        APR_LAUNCH_CHECK();
+        return APR_OK;
+      };
+      constexpr size_t kNG = sizeof(kGraphGroups) / sizeof(int);
+      GraphEntry* by_size[kNG];
+      for (size_t k = 0; k < kNG; ++k) {
+        by_size[k] = graph_find(ax, key, fn, kGraphGroups[k]);
+        if (!by_size[k]) {
+          const int rc = graph_build(ax, key, fn, kGraphGroups[k], topo, issue_group, &by_size[k]);
+          if (rc) return rc;
         }
       }
-      if (e2 == cudaSuccess && !sl.exec) e2 = cudaGraphInstantiate(&sl.exec, graph, 0);
-      if (e2 == cudaSuccess) e2 = cudaGraphLaunch(sl.exec, st);
-      if (e2 == cudaSuccess) e2 = cudaEventRecord(sl.done, st);
-      cudaGraphDestroy(graph);
-      if (e2 != cudaSuccess) { set_cuda_error(e2, "CUDA graph replay"); return APR_E_CUDA; }
+      dyn_set_kernel<<<1, 1, 0, st>>>(const_cast<StepDyn*>(dyn_dev), c.s_begin, c.stats);
+      APR_LAUNCH_CHECK();
+      int left = c.s_end - c.s_begin;
+      for (size_t k = 0; k < kNG; ++k) {
+        while (left >= kGraphGroups[k]) {
+          GraphEntry* e = by_size[k];
+          APR_CUDA_CHECK(cudaGraphLaunch(e->exec, st));
+          APR_CUDA_CHECK(cudaEventRecord(e->done, st));
+          e->last_use = ++ax.graph_clock;
+          ++ax.graph_launches;
+          left -= kGraphGroups[k];
+        }
+      }
       return APR_OK;
     }
-    return issue(st);
+    return issue_steps(c, st, c.s_begin, c.s_end);
   }
   if (mode == 2) {
     // small batches (tables in L2, steps of a few microseconds): ONE cluster of up to 16 CTAs runs every step of the
@@ -1340,20 +1391,21 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st) {
 }
 
 template <int G, int V>
-static int run_steps(const StepCtx& c, int mode, cudaStream_t st) {
-  if (c.d == G * V * 4) return run_steps_t<G, V, true>(c, mode, st);
-  return run_steps_t<G, V, false>(c, mode, st);
+static int run_steps(const StepCtx& c, int mode, cudaStream_t st, const StepDyn* dyn_dev) {
+  if (c.d == G * V * 4) return run_steps_t<G, V, true>(c, mode, st, dyn_dev);
+  return run_steps_t<G, V, false>(c, mode, st, dyn_dev);
 }
 
-static int dispatch_steps(const StepCtx& c, int mode, cudaStream_t st) {
+// dyn_dev: device StepDyn of the workspace (graph replay allowed) or nullptr (plain launches only)
+static int dispatch_steps(const StepCtx& c, int mode, cudaStream_t st, const StepDyn* dyn_dev) {
   const int q = c.d / 4;
-  if (q <= 4) return run_steps<4, 1>(c, mode, st);
-  if (q <= 8) return run_steps<8, 1>(c, mode, st);
-  if (q <= 16) return run_steps<16, 1>(c, mode, st);
-  if (q <= 32) return run_steps<32, 1>(c, mode, st);
-  if (q <= 64) return run_steps<32, 2>(c, mode, st);
-  if (q <= 96) return run_steps<32, 3>(c, mode, st);
-  return run_steps<32, 4>(c, mode, st);
+  if (q <= 4) return run_steps<4, 1>(c, mode, st, dyn_dev);
+  if (q <= 8) return run_steps<8, 1>(c, mode, st, dyn_dev);
+  if (q <= 16) return run_steps<16, 1>(c, mode, st, dyn_dev);
+  if (q <= 32) return run_steps<32, 1>(c, mode, st, dyn_dev);
+  if (q <= 64) return run_steps<32, 2>(c, mode, st, dyn_dev);
+  if (q <= 96) return run_steps<32, 3>(c, mode, st, dyn_dev);
+  return run_steps<32, 4>(c, mode, st, dyn_dev);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1548,7 +1600,7 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = s_begin; c.s_end = s_end;
-  return dispatch_steps(c, mode, st);
+  return dispatch_steps(c, mode, st, reinterpret_cast<const StepDyn*>(at<char>(ws, L.off_hdr) + kDynOffset));
 }
 
 int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
@@ -1561,8 +1613,10 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
-  // same sub-chunk granularity as apr_train_steps (mode 0: the same launch sequences, hence the same CUDA graphs)
   const int sub = mode == 0 ? L.Sc : S;
   for (int s0 = 0; s0 < S; s0 += sub) {
     rc = run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, s0, std::min(S, s0 + sub), st);
@@ -1584,27 +1638,34 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  AuxStream& ax = aux_stream();
-  if (!ax.ok) return APR_E_CUDA;
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  DeviceContext& ax = *ctx;
+  std::lock_guard<std::recursive_mutex> lk(ax.mu);
   if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
   // everything already enqueued on the caller's stream (producers of u,i,j; earlier steps reading the arrays) first
   APR_CUDA_CHECK(cudaEventRecord(ax.entry, st));
   APR_CUDA_CHECK(cudaStreamWaitEvent(ax.prep_stream, ax.entry, 0));
   rc = prepare_clear(L, ws, ax.prep_stream);
   if (rc) return rc;
-  const int nsub = (S + L.Sc - 1) / L.Sc;
-  for (int k = 0; k < nsub; ++k) {
-    const int s0 = k * L.Sc, ns = std::min(L.Sc, S - s0);
-    rc = prepare_sub(u, i, j, L, s0, ns, rows_p, rows_q, ws, ax.prep_stream, pairs_enabled(d));
+  // sub-chunks of 2, 4, 8, ... up to Sc steps: only the index preparation of the FIRST sub-chunk is exposed in front of
+  // the step kernels (it cannot start before the previous call's steps have released the per-step arrays), so it is
+  // kept short; every later one runs under the steps of its predecessor
+  std::vector<int> sizes;
+  for (int left = S, n = std::min(2, L.Sc); left > 0; n = std::min(L.Sc, 2 * n)) {
+    sizes.push_back(std::min(left, n));
+    left -= sizes.back();
+  }
+  for (size_t k = 0, s0 = 0; k < sizes.size(); s0 += sizes[k], ++k) {
+    rc = prepare_sub(u, i, j, L, int(s0), sizes[k], rows_p, rows_q, ws, ax.prep_stream, pairs_enabled(d));
     if (rc) return rc;
-    cudaEvent_t e = ax.prep_event(size_t(k));
+    cudaEvent_t e = ax.prep_event(k);
     if (!e) return APR_E_CUDA;
     APR_CUDA_CHECK(cudaEventRecord(e, ax.prep_stream));
   }
-  for (int k = 0; k < nsub; ++k) {
-    const int s0 = k * L.Sc, ns = std::min(L.Sc, S - s0);
-    APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.prep_event(size_t(k)), 0));
-    rc = run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, s0, s0 + ns, st);
+  for (size_t k = 0, s0 = 0; k < sizes.size(); s0 += sizes[k], ++k) {
+    APR_CUDA_CHECK(cudaStreamWaitEvent(st, ax.prep_event(k), 0));
+    rc = run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, adver, mode, ws, L, stats, int(s0), int(s0) + sizes[k], st);
     if (rc) return rc;
   }
   return APR_OK;
@@ -1642,6 +1703,9 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 4) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
   if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
   StepCtx c;
   memset(&c, 0, sizeof(c));
   for (int r = 0; r < nranks; ++r) {
@@ -1664,7 +1728,7 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = step; c.s_end = step + 1; c.only_stage = stage; c.cluster_sync = 0;
-  return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream));
+  return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 // Cross-rank barrier on peer-mapped signal words: rank r stores `epoch` into slot [r] of every peer's signal array and
@@ -1689,8 +1753,6 @@ __global__ void xbarrier_launch(SigArray sig, int nranks, int rank, int epoch, i
   __threadfence_system();
 }
 
-static int g_xbarrier_epoch = 0;
-
 // Steps [first_step, first_step+count) on row-sharded tables, everything launched from here: per step the fast kernel on
 // the second stream, the general stages on the caller's stream with a cross-rank barrier after the plain stage, after
 // the adversarial stage and at the end of the step.  sig = nranks peer pointers to >= nranks ints each (zeroed once);
@@ -1701,14 +1763,16 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
                             void* ws, int64_t ws_bytes, float* stats, int32_t first_step, int32_t count, int32_t* err,
                             apr_stream_t stream) {
   if (!sig || !err || count < 1 || first_step < 0 || first_step + count > S) return APR_E_ARG;
-  AuxStream& ax = aux_stream();
-  if (!ax.ok) return APR_E_CUDA;
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  DeviceContext& ax = *ctx;
+  std::lock_guard<std::recursive_mutex> lk(ax.mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SigArray sa;
   for (int r = 0; r < kMaxRanks; ++r) sa.p[r] = r < nranks ? sig[r] : nullptr;
   auto barrier = [&]() -> int {
     if (nranks == 1) return APR_OK;
-    xbarrier_launch<<<1, 32, 0, st>>>(sa, nranks, rank, ++g_xbarrier_epoch, err);
+    xbarrier_launch<<<1, 32, 0, st>>>(sa, nranks, rank, ++ax.xbarrier_epoch, err);
     APR_LAUNCH_CHECK();
     return APR_OK;
   };
@@ -1725,13 +1789,13 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
     static const int order = env_int("APR_SHARD_ORDER", 0);
     auto launch_fast = [&]() -> int {
       APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
-      APR_CUDA_CHECK(cudaStreamWaitEvent(ax.stream, ax.fork, 0));
-      if (timing) cudaEventRecord(ev[6], ax.stream);
+      APR_CUDA_CHECK(cudaStreamWaitEvent(ax.fast_stream, ax.fork, 0));
+      if (timing) cudaEventRecord(ev[6], ax.fast_stream);
       const int r2 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
-                                             adver, ws, ws_bytes, stats, s, 3, ax.stream);
+                                             adver, ws, ws_bytes, stats, s, 3, ax.fast_stream);
       if (r2) return r2;
-      APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.stream));
-      if (timing) cudaEventRecord(ev[7], ax.stream);
+      APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.fast_stream));
+      if (timing) cudaEventRecord(ev[7], ax.fast_stream);
       if (pairs_enabled(d)) {   // pair work units: third stream, no ordering against the other kernels of the step
         APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
         const int r3 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,

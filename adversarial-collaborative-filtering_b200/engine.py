@@ -45,6 +45,14 @@ def device_info() -> Tuple[int, int, int]:
     return a.value, b.value, c.value
 
 
+def context_stats() -> dict:
+    """Graph-cache counters of the current device's library context (see include/apr_b200.h)."""
+    out = (ctypes.c_int64 * 4)()
+    _lib.check(_lib.lib().apr_context_stats(out))
+    return {"graph_instantiations": int(out[0]), "graph_updates": int(out[1]), "graph_launches": int(out[2]),
+            "graphs_cached": int(out[3])}
+
+
 def init_truncated_normal(W: torch.Tensor, stddev: float, seed: int, table_id: int, tag: int = STREAM_INIT) -> None:
     rows, d = W.shape
     _lib.check(_lib.lib().apr_init_truncated_normal(_ptr(W, torch.float32), rows, d, float(stddev), seed & 0xFFFFFFFF,

@@ -133,7 +133,9 @@ def cpu_port():
     """(step function, threads, label): the C/OpenMP restatement when it builds, else the NumPy oracle (1 thread)."""
     try:
         from oracle import c_oracle as C
-        n = C.threads()
+        # explicit thread count: torchrun exports OMP_NUM_THREADS=1 to every rank, which made the round-1 reference arm
+        # single-threaded at N >= 2
+        n = C.set_threads(int(os.environ.get("APR_BENCH_CPU_THREADS", os.cpu_count() or 1)))
         return (lambda O, P, Q, aP, aQ, u, i, j, lr, reg, ra, eps, adv: C.step(P, Q, aP, aQ, u, i, j, lr, reg, ra, eps, adv),
                 n, "C/OpenMP oracle port (oracle/apr_oracle_c.c), %d threads" % n)
     except Exception as e:  # no compiler / no OpenMP: the NumPy oracle
@@ -367,27 +369,31 @@ def main_single(args):
     def run_chunk(u, i, j):
         engine.train_steps(P, Q, aP, aQ, u, i, j, *hp, ws, mode=args.mode)
 
-    # ---- warm-up ---------------------------------------------------------------------------------------
-    done = 0
-    while done < W:
-        n = min(CH, W - done)
-        run_chunk(*device_chunk(n))
-        done += n
-    torch.cuda.synchronize()
-
-    # ---- timed region: K steps, ids resident in HBM -----------------------------------------------------
+    # ---- timed-region inputs: K steps, ids resident in HBM -----------------------------------------------
     chunks = []
     left = K
     while left > 0:
         n = min(CH, left)
         chunks.append(device_chunk(n))
         left -= n
+
+    # ---- warm-up: W steps, then one call of every chunk SHAPE the timed region uses (so that whatever a call
+    # shape builds lazily -- executable CUDA graphs, stream/event pools, kernel attributes -- exists before the clock starts)
+    done = 0
+    while done < W:
+        n = min(CH, W - done)
+        run_chunk(*device_chunk(n))
+        done += n
+    for n in sorted({c[0].shape[0] for c in chunks}):
+        run_chunk(*device_chunk(n))
+        done += n
+    warmup_run = done
+    torch.cuda.synchronize()
+    ctx0 = engine.context_stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -395,14 +401,9 @@ def main_single(args):
         run_chunk(*c)
     ev1.record()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ctx1 = engine.context_stats()
     value = world * K * B / (ms * 1e-3)
     pairs_on = d <= 128 and os.environ.get("APR_PAIRS", "1") != "0"   # pair work units (csrc/train.cu: pairs_enabled)
 
@@ -411,7 +412,11 @@ def main_single(args):
         sc = max(1, min(S, (48 << 20) // ((max(32, 2 * p2) + max(32, 4 * p2)) * 8)))
         prep = 5 if pairs_on else 4      # insert, compact, scatter, [pair detection], pack
         step = 5 if pairs_on else 4      # fast kernel, [pair kernel], three general stages
-        return prep * -(-S // sc) + (1 if args.mode in (1, 2) else step * S)
+        nsub, left, n = 0, S, min(2, sc)          # sub-chunks of 2, 4, 8, ... sc steps (apr_train_steps)
+        while left > 0:
+            nsub, left, n = nsub + 1, left - min(left, n), min(sc, 2 * n)
+        # graph replay adds one cursor-advance node per group of 8/4/2/1 steps and one cursor-set launch per sub-chunk
+        return prep * nsub + (nsub if args.mode in (1, 2) else step * S + S // 8 + bin(S % 8).count("1") + nsub)
     launches = sum(n_launches(c[0].shape[0]) for c in chunks)
 
     # ---- roofline of the dominant kernel(s): the embedding step kernels, index preparation excluded -------
@@ -434,15 +439,17 @@ def main_single(args):
         bytes_total += float(16 * d * cnt.sum() + 12 * B * c[0].shape[0])
     achieved = bytes_total / (ms_run * 1e-3) / 1e9
     steps_roof = sum(c[0].shape[0] for c in chunks[:n_roof])
-    # traffic: dram__bytes_read+write per step from the ncu capture of this command (profiles/r1m_launches_mode0_B65536_pairs.csv:
-    # fast_kernel 177.2 + 114.3 MB, pair_kernel 18.1 MB, 3 general stages 2.5 MB each; serialised cold-cache replay, the
-    # late write-backs of the small kernels are not attributed to them)
+    bytes_step = bytes_total / steps_roof
+    whole = bytes_step / (ms / K * 1e-3) / 1e9        # the same bytes over the TIMED region's ms_per_step (index preparation included)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 317.1e6 if (B == 65536 and d == 128 and args.mode == 0 and pairs_on) else None, "peak_kind": peak_kind,
+                "frac_kind": "kernel-only: the step kernels of an already prepared chunk (apr_train_run), CUDA events",
+                "whole_step_achieved": whole, "whole_step_frac": whole / hbm_peak,
+                "whole_step_kind": "bytes_per_step_model / ms_per_step of the timed region (index preparation + step kernels)",
+                "traffic": measured_traffic(B, d, args.mode), "peak_kind": peak_kind,
                 "kernel": "step_persistent_kernel" if args.mode in (1, 2) else
                 ("fast_kernel || pair_kernel || 3 x general_stage_kernel per step" if pairs_on else
                  "fast_kernel || 3 x general_stage_kernel per step"),
-                "bytes_per_step_model": bytes_total / steps_roof, "ms_per_step_kernel": ms_run / steps_roof}
+                "bytes_per_step_model": bytes_step, "ms_per_step_kernel": ms_run / steps_roof}
 
     # ---- e2e: public API with HOST batches; H2D of ids and D2H of the per-step loss inside the region ------
     Ke = min(K, 4 * CH)
@@ -472,7 +479,11 @@ def main_single(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args), "roofline": roofline, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "warmup_steps_run": warmup_run,
+            "graph_cache": {"instantiations_in_timed_region": ctx1["graph_instantiations"] - ctx0["graph_instantiations"],
+                            "updates_in_timed_region": ctx1["graph_updates"] - ctx0["graph_updates"],
+                            "launches_in_timed_region": ctx1["graph_launches"] - ctx0["graph_launches"],
+                            "cached": ctx1["graphs_cached"]}}
 
     # ---- SURVEY 8(d) variants on the same tables: batch sweep 2^9 .. 2^20 and the Zipf(1.05)-items contention case ---
     if not args.no_variants and rank == 0:
@@ -500,6 +511,22 @@ def main_single(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_traffic(B, d, mode):
+    """DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the step's kernels) from the committed ncu
+    capture of this workload, or None: profiles/traffic.json = [{"batch", "d", "mode", "bytes_per_step", "source"}, ...]
+    written from the `ncu --set full` CSV named in "source" (never a number typed in by hand)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        for r in json.load(open(p)):
+            if r.get("batch") == B and r.get("d") == d and r.get("mode") == mode:
+                return float(r["bytes_per_step"])
+    except Exception:
+        return None
+    return None
 
 
 def zipf_items(rng, shape, items, s=1.05):

@@ -44,6 +44,17 @@ const char* apr_last_cuda_error(void);
 /* sm count / compute capability of the current device. */
 int apr_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 
+/* Per-device host state (side streams, fork/join events, the cache of executable CUDA graphs of the training step,
+ * the cross-rank barrier epoch, the evaluation timing events) lives in one context per CUDA device, created on the
+ * first call made while that device is current; entry points that use it are serialised per device (the reference
+ * drives its session from one host thread).  apr_context_create builds it ahead of time (so that no
+ * stream / event creation lands inside a timed call), apr_context_destroy releases it (after the device is idle).
+ * apr_context_stats (current device): out4_host = {graph instantiations, in-place graph updates, graph launches,
+ * cached executable graphs} since the context was created -- bench.py reports the first two across its timed region. */
+int apr_context_create(int32_t device);
+int apr_context_destroy(int32_t device);
+int apr_context_stats(int64_t* out4_host);
+
 /* ---- A1 / K12: MF._create_variables, APR.py:105-119 (tf.truncated_normal(mean 0, stddev)) and the
  *      `--adv random` noise of APR.py:172-177.  Philox4x32-10, counter (e_lo, e_hi, attempt, table_id),
  *      key (seed, stream_tag); see oracle/apr_oracle.py:truncated_normal. */

@@ -41,6 +41,15 @@ int apr_oracle_threads(void) {
 #endif
 }
 
+/* explicit thread count (torchrun exports OMP_NUM_THREADS=1 to its children: the bench overrides it) */
+void apr_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* u,i,j: [B] row ids into P / Q.  Returns 0, or -1 on allocation failure. */
 int apr_oracle_step(float* P, float* Q, float* accP, float* accQ, int d, const int32_t* u, const int32_t* i,
                     const int32_t* j, int B, float lr, float reg, float reg_adv, float eps, int adver) {

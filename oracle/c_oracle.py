@@ -30,6 +30,12 @@ def threads() -> int:
     return int(load().apr_oracle_threads())
 
 
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads from now on (whatever OMP_NUM_THREADS says); returns the count in effect."""
+    load().apr_oracle_set_threads(ctypes.c_int(int(n)))
+    return threads()
+
+
 def step(P, Q, aP, aQ, u, i, j, lr, reg, reg_adv, eps, adver) -> None:
     """In place on float32 C-contiguous tables; u, i, j int32 [B]."""
     u, i, j = [np.ascontiguousarray(x, dtype=np.int32).reshape(-1) for x in (u, i, j)]
