@@ -88,6 +88,8 @@ _SIGNATURES = {
     "apr_fill_f32": (ctypes.c_int, [_P, c_int64, c_float, _P]),
     "apr_sample_epoch": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_uint32, c_uint32, c_int32,
                                         _P, _P, _P, _P, _P, _P]),
+    "apr_sample_epoch_shard": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_uint32, c_uint32, c_int32,
+                                              c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
     "apr_select_dns": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int32, _P, _P]),
     "apr_train_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "apr_train_workspace_init": (ctypes.c_int, [_P, c_int64, _P]),
@@ -115,7 +117,11 @@ _SIGNATURES = {
     "apr_eval_tc_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "apr_eval_fullrank_tc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int64, _P,
                                             _P]),
-    "apr_eval_tc_ambiguous": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
+    "apr_eval_tc_topk_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "apr_eval_fullrank_tc_topk": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, c_int32, _P, _P,
+                                                 _P, ctypes.c_uint64, _P, _P, c_int64, _P, _P]),
+    "apr_eval_tc_ambiguous": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
+    "apr_topk_merge": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "apr_eval_tc_timing": (ctypes.c_int, [c_int32, POINTER(c_float)]),
     "apr_sum_squares": (ctypes.c_int, [_P, c_int64, _P, _P]),
 }

@@ -384,7 +384,17 @@ int apr_eval_fullrank(const float* P, const float* Q, int32_t d, const int32_t* 
   if (n_users < 1 || item_hi <= item_lo || item_lo < 0 || k_top < 0 || k_top > 128 || !valid_dim(d)) return APR_E_ARG;
   if (k_top > 0 && (!topk_ids || !topk_scores)) return APR_E_ARG;
   if (!aligned16(P) || !aligned16(Q)) return APR_E_ALIGN;
-  (void)exact;
+  if (!exact && (d % 8) == 0 && d <= 256 && (reinterpret_cast<uintptr_t>(ws) & 1023u) == 0) {
+    // tensor-core route (same results): taken when the caller's workspace is large enough for it; the pipeline error
+    // flag of that path (never set in a healthy run) is the int32 right behind the tensor-core layout
+    const int64_t need = apr_eval_tc_topk_workspace_bytes(n_users, item_hi - item_lo, d, k_top);
+    if (need > 0 && ws_bytes >= need + 1024) {
+      int32_t* err = reinterpret_cast<int32_t*>(static_cast<char*>(ws) + need);
+      APR_CUDA_CHECK(cudaMemsetAsync(err, 0, 4, static_cast<cudaStream_t>(stream)));
+      return apr_eval_fullrank_tc_topk(P, Q, d, users, test_item, n_users, item_lo, item_hi, excl_ptr, excl_idx, k_top, position,
+                                       topk_ids, topk_scores, 0, nullptr, ws, need, err, stream);
+    }
+  }
   return eval_fullrank_exact(P, Q, d, users, test_item, n_users, item_lo, item_hi, excl_ptr, excl_idx, k_top, position,
                              topk_ids, topk_scores, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }

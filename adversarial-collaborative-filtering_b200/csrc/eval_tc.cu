@@ -25,6 +25,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -40,11 +41,6 @@ constexpr int TC_NORM_SLOTS = 8;         // smem ring of item-norm blocks (0 slo
 constexpr int TC_THREADS = 576;            // warps 0-15 epilogue (four per TMEM lane quarter), warp 16 TMA producer, warp 17 MMA
 constexpr int TC_PRODUCER_WARP = 16;
 constexpr int TC_MMA_WARP = 17;            // highest warp id: the scheduler favours it, and MMA issue is the critical chain
-// capacity of the ambiguous list: max(256, n_items / 256) pairs per user (~0.4 % of all pairs; ~0.07-0.2 % are expected)
-static inline int64_t tc_amb_cap(int n_users, int n_items) {
-  return std::min<int64_t>(int64_t(n_users) * std::max(256, n_items / 256), 0x7fffff00);
-}
-
 // split2 (d % 64 == 0): both operands are stored as [hi | lo] (K' = 2d) and the b_hi stage is multiplied with a_hi AND
 // a_lo, the b_lo stage with a_hi -- the same three products with a third less operand traffic and shared memory.
 // Otherwise K' = 3d: A' = [hi | hi | lo], B' = [hi | lo | hi], zero padded to a multiple of 64.
@@ -150,7 +146,10 @@ tc_prep_split2_kernel(const float* __restrict__ T, const int32_t* __restrict__ r
 }
 
 // per item tile: maxima of the norms of its four 32-column blocks, stored behind the 128 norms
-__global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles, int nchunk, int64_t tile_bytes) {
+// (+ the maximum over ALL items of the range -> qmax_all[0], the top-k threshold's error bound; norms are >= 0, so the
+// unsigned order of their bit patterns is their numeric order and a poisoned Inf block stays the maximum)
+__global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles, int nchunk, int64_t tile_bytes,
+                                   unsigned* __restrict__ qmax_all) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles * 4) return;
   float* nb = reinterpret_cast<float*>(img + int64_t(t >> 2) * tile_bytes + int64_t(nchunk) * TC_CHUNK_BYTES);
@@ -160,6 +159,7 @@ __global__ void tc_norm_max_kernel(unsigned char* __restrict__ img, int n_tiles,
     m = (x < CUDART_INF_F) ? fmaxf(m, x) : CUDART_INF_F;   // NaN / Inf norms poison the block maximum on purpose
   }
   nb[128 + (t & 3)] = m;
+  atomicMax(qmax_all, __float_as_uint(m));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -252,13 +252,22 @@ constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((T
 // ------------------------------------------------------------------------------------------------
 // NCHUNK / CPS > 0: the chunk layout is a compile-time constant (d = 64, 128, 256) and the MMA issue loop unrolls into
 // straight-line code with constant A-descriptor offsets; NCHUNK == 0 is the generic (runtime layout) instantiation.
-template <int NCHUNK, int CPS>
+// MODE (the epilogue; the TMA / MMA pipeline is the same):
+//   TC_COUNT    position counts + ambiguous list against spos (above)
+//   TC_COUNT_GM the same, and every epilogue thread also keeps the maxima of its eight 4-column groups over all the
+//               tiles of the CTA -> gmax[user][32 * splits]: 32 * splits scores of DISTINCT items per user, from which
+//               tc_topk_threshold_kernel derives a lower bound tau_u of the user's k-th best exact score
+//   TC_COLLECT  spos := tau; every (user, item) with s_tc >= tau_u - E goes to the CTA's list segment (the top-k candidates)
+constexpr int TC_COUNT = 0, TC_COUNT_GM = 1, TC_COLLECT = 2;
+constexpr int TC_GROUPS_PER_CTA = 32;   // group maxima per user row and CTA: 4 column blocks x 8 groups of 4 columns
+
+template <int NCHUNK, int CPS, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int nchunk_rt,
                 int64_t tile_bytes, int nstage, int norm_slots, int cps_rt, int n_users, const float* __restrict__ spos,
                 const float* __restrict__ user_scale, int item_lo, int item_hi, int tiles_total, int tiles_per_cta,
                 int32_t* __restrict__ position, int2* __restrict__ amb, int* __restrict__ amb_count, int amb_cap,
-                int* __restrict__ err) {
+                float* __restrict__ gmax, int* __restrict__ err) {
   const int nchunk = NCHUNK ? NCHUNK : nchunk_rt;
   const int cps = NCHUNK ? CPS : cps_rt;
   extern __shared__ unsigned char smem_raw[];
@@ -389,6 +398,9 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
     int2* my_amb = amb + int64_t(cta) * amb_cap;           // amb_cap = capacity of ONE CTA's segment
     int cnt = 0;
     bool ok = true;
+    float gm[8];            // TC_COUNT_GM: running maxima of this thread's eight 4-column groups
+#pragma unroll
+    for (int g = 0; g < 8; ++g) gm[g] = -CUDART_INF_F;
     int nslot = 0;          // norm ring position of tile t (t % norm_slots) and its phase, kept without dividing
     uint32_t nphase = 0;
     for (int t = 0; t < ntile && ok; ++t) {
@@ -416,7 +428,39 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
         float E = fmaf(gue * qmax, 1.0f + 0x1p-21f, 1e-30f);
         if (!(E < 1e30f)) E = CUDART_INF_F;               // non-finite / near-overflow magnitudes: no sign-bit arithmetic
         const int ncols = item_hi - (n0 + col0);           // columns past item_hi (padding of the last tile) never count
-        if (ncols >= 32 && qmax < CUDART_INF_F && E < CUDART_INF_F) {   // uniform except for degenerate users
+        if (MODE == TC_COLLECT) {
+          // candidates of the top-k: s_tc >= tau - E  <=>  tau - s_tc <= E (tau = +inf: user handled by the fallback kernel)
+          const float Ec = fminf(E, 1e30f);
+          if (ncols >= 32) {
+            float mn[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) mn[jx >> 3] = fminf(mn[jx >> 3], sp - v[jx]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (mn[g] <= Ec && uvalid) {
+#pragma unroll
+                for (int jx = 8 * g; jx < 8 * g + 8; ++jx) {
+                  if (sp - v[jx] <= Ec) {
+                    const int slot = atomicAdd(&s_amb_count, 1);
+                    if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
+                  }
+                }
+              }
+            }
+          } else if (ncols > 0 && uvalid) {
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) {
+              if (jx < ncols && sp - v[jx] <= Ec) {
+                const int slot = atomicAdd(&s_amb_count, 1);
+                if (slot < amb_cap) my_amb[slot] = make_int2(uidx, n0 + col0 + jx);
+              }
+            }
+          }
+        } else if (ncols >= 32 && qmax < CUDART_INF_F && E < CUDART_INF_F) {   // uniform except for degenerate users
+          if (MODE == TC_COUNT_GM) {
+#pragma unroll
+            for (int jx = 0; jx < 32; ++jx) gm[jx >> 2] = fmaxf(gm[jx >> 2], v[jx]);
+          }
           unsigned c = 0u;
           float mg[4] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
 #pragma unroll
@@ -444,6 +488,7 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
 #pragma unroll
           for (int jx = 0; jx < 32; ++jx) {
             if (jx >= ncols) continue;
+            if (MODE == TC_COUNT_GM) gm[jx >> 2] = fmaxf(gm[jx >> 2], v[jx]);
             const float Ej = fmaf(gue * qn[col0 + jx], 1.0f + 0x1p-21f, 1e-30f);
             const float w = v[jx] - sp;
             const bool undecidable = !(Ej < 1e30f);      // NaN / Inf / near-overflow: the exact chain decides, whatever w is
@@ -458,7 +503,12 @@ tc_count_kernel(const unsigned char* __restrict__ a_img, const unsigned char* __
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
-    if (uvalid && cnt) atomicAdd(&position[uidx], cnt);
+    if (MODE != TC_COLLECT && uvalid && cnt) atomicAdd(&position[uidx], cnt);
+    if (MODE == TC_COUNT_GM && uvalid) {
+      float4* dst = reinterpret_cast<float4*>(gmax + (int64_t(uidx) * gridDim.y + blockIdx.y) * TC_GROUPS_PER_CTA + (col0 >> 5) * 8);
+      dst[0] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+      dst[1] = make_float4(gm[4], gm[5], gm[6], gm[7]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -523,20 +573,291 @@ tc_rescore_group_kernel(const float* __restrict__ P, const float* __restrict__ Q
   }
 }
 
-struct TcWs { int64_t off_spos, off_scale, off_aimg, off_bimg, off_amb, off_cnt, total; int n_utiles, n_itiles; };
-static TcWs tc_ws(int n_users, int n_items, int d) {
+
+// ------------------------------------------------------------------------------------------------
+// top-k on the tensor-core path (K9 epilogue + K10 merge; evaluation.py:54-76 heapq.nlargest order, utils.py:244-261)
+// ------------------------------------------------------------------------------------------------
+constexpr int TOPK_UCAP = 1024;     // per-user candidate buffer of the tensor-core top-k (entries that survive exact re-scoring)
+
+__device__ __forceinline__ uint32_t float_key(float x) {      // monotone map float -> uint32 (larger float, larger key)
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// One warp per user: r = k_top + |excl(u)|; t_r = the r-th largest of the user's G group maxima (each is the tensor-core
+// score of a distinct item).  Every one of those r items has an exact score >= t_r - E_u and at most |excl(u)| of them
+// are excluded, so the user's k-th best exact score among the candidates is >= tau_u = t_r - E_u: tau_u is the pass-B
+// threshold.  Fewer than r finite maxima (tiny catalogue, user with a huge train list) or non-finite values -> tau = +inf and
+// the user is flagged for the exact per-user kernel.
+__global__ void __launch_bounds__(256)
+tc_topk_threshold_kernel(const float* __restrict__ gmax, int G, int n_users, int k_top, const int64_t* __restrict__ excl_ptr,
+                         const float* __restrict__ user_scale, const float* __restrict__ qmax_all, float* __restrict__ tau,
+                         int* __restrict__ fallback) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_users) return;
+  const float* g = gmax + int64_t(warp) * G;
+  const int r = k_top + int(excl_ptr[warp + 1] - excl_ptr[warp]);
+  int finite = 0;
+  for (int e = lane; e < G; e += 32) finite += (fabsf(g[e]) < CUDART_INF_F) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(0xffffffffu, finite, o);
+  const float Eu = user_scale[warp] * qmax_all[0] * 1.0001f;
+  bool fb = finite < r || !(Eu < 1e30f);
+  float t = CUDART_INF_F;
+  if (!fb) {
+    uint32_t T = 0u;   // largest key with count(key >= T over the finite maxima) >= r
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      for (int e = lane; e < G; e += 32) { const float x = g[e]; c += (fabsf(x) < CUDART_INF_F && float_key(x) >= cand) ? 1 : 0; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (c >= r) T = cand;
+    }
+    const float tr = key_float(T);
+    t = tr - Eu;
+    t = t - fabsf(t) * 2.4e-7f - 1e-30f;     // the roundings of the two subtractions, downwards
+    if (!(fabsf(t) < CUDART_INF_F)) { fb = true; t = CUDART_INF_F; }
+  }
+  if (lane == 0) { tau[warp] = t; fallback[warp] = fb ? 1 : 0; }
+}
+
+// exact re-scoring of the pass-B candidates (same 8-lanes-per-pair chain as tc_rescore_group_kernel); survivors (not
+// excluded, exact score >= tau_u) are appended to the user's buffer.  A CTA list segment that overflowed flags the 128
+// users of its tile for the exact per-user kernel.
+__global__ void __launch_bounds__(512)
+tc_topk_rescore_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
+                       int n_users, const float* __restrict__ tau, const int2* __restrict__ amb, const int* __restrict__ amb_count,
+                       int amb_cap, int n_utiles, const int64_t* __restrict__ excl_ptr, const int32_t* __restrict__ excl_idx,
+                       float* __restrict__ ubuf_score, int32_t* __restrict__ ubuf_id, int* __restrict__ ucount,
+                       int* __restrict__ fallback) {
+  const int seg = blockIdx.y;
+  const int n_raw = amb_count[seg];
+  if (n_raw > amb_cap && blockIdx.x == 0) {
+    const int m0 = (seg % n_utiles) * TC_BM;
+    for (int m = threadIdx.x; m < TC_BM; m += blockDim.x) if (m0 + m < n_users) fallback[m0 + m] = 1;
+  }
+  const int n = min(n_raw, amb_cap);
+  if (int(blockIdx.x * (blockDim.x >> 3)) >= n) return;
+  const int d4 = d >> 2;
+  const int2* list = amb + int64_t(seg) * amb_cap;
+  const int lane = threadIdx.x & 31, s8 = lane & 7, gbase = lane & ~7;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ngroups = (gridDim.x * blockDim.x) >> 3;
+  const int nlines = (d4 + 7) >> 3;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = group - (lane >> 3); t0 < n; t0 += ngroups) {
+    const int t = t0 + (lane >> 3);
+    const bool valid = t < n;
+    const int2 a = list[valid ? t : t0];
+    const float4* p4 = reinterpret_cast<const float4*>(P + int64_t(users[a.x]) * d);
+    const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(a.y) * d);
+    float acc = 0.f;
+    for (int l0 = 0; l0 < nlines; l0 += 4) {
+      float4 x[4], y[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int e = (l0 + l) * 8 + s8;
+        const bool in = (l0 + l) < nlines && e < d4;
+        y[l] = in ? __ldg(q4 + e) : zero4;
+        x[l] = in ? __ldg(p4 + e) : zero4;
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (l0 + l < nlines) {
+#pragma unroll
+          for (int st = 0; st < 8; ++st) {
+            float v = fmaf(x[l].x, y[l].x, acc);
+            v = fmaf(x[l].y, y[l].y, v);
+            v = fmaf(x[l].z, y[l].z, v);
+            v = fmaf(x[l].w, y[l].w, v);
+            acc = __shfl_sync(0xffffffffu, v, gbase | st);
+          }
+        }
+      }
+    }
+    if (valid && s8 == 0 && acc >= tau[a.x]) {
+      // excluded items (train items, the held-out item) are not candidates: sorted CSR row, binary search
+      int64_t lo = excl_ptr[a.x], hi = excl_ptr[a.x + 1];
+      const int64_t end = hi;
+      while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (excl_idx[m] < a.y) lo = m + 1; else hi = m; }
+      if (!(lo < end && excl_idx[lo] == a.y)) {
+        const int slot = atomicAdd(&ucount[a.x], 1);
+        if (slot < TOPK_UCAP) { ubuf_score[int64_t(a.x) * TOPK_UCAP + slot] = acc; ubuf_id[int64_t(a.x) * TOPK_UCAP + slot] = a.y; }
+      }
+    }
+  }
+}
+
+// K10: per user, the k best of up to m (score, id) entries by (score desc, id asc); id < 0 = padding.  Rank by counting
+// in shared memory (m <= 1024).  One CTA per user.  Used for the per-user candidate buffers (counts != nullptr: the
+// number of valid entries per user; a count > m or flags[u] != 0 leaves the user to the exact per-user kernel) and as
+// the cross-shard merge (apr_topk_merge: counts = flags = nullptr, rows of m = shards * k entries).
+__global__ void __launch_bounds__(128)
+topk_select_kernel(const float* __restrict__ in_score, const int32_t* __restrict__ in_id, int m, const int* __restrict__ counts,
+                   int* __restrict__ flags, int k, int32_t* __restrict__ out_id, float* __restrict__ out_score) {
+  __shared__ float ss[TOPK_UCAP];
+  __shared__ int si[TOPK_UCAP];
+  const int u = blockIdx.x;
+  int n = m;
+  if (counts) {
+    n = counts[u];
+    if (n > m) { if (threadIdx.x == 0) flags[u] = 1; return; }   // buffer overflow
+  }
+  if (flags && flags[u]) return;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    ss[e] = in_score[int64_t(u) * m + e];
+    si[e] = in_id[int64_t(u) * m + e];
+  }
+  __shared__ int s_nvalid;
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  int n_valid = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float se = ss[e];
+    const int ie = si[e];
+    if (ie < 0) continue;
+    ++n_valid;
+    int rank = 0;
+    for (int f = 0; f < n; ++f) {
+      const float sf = ss[f];
+      const int jf = si[f];
+      rank += (jf >= 0) && ((sf > se) || (sf == se && jf < ie));
+    }
+    if (rank < k) { out_id[int64_t(u) * k + rank] = ie; out_score[int64_t(u) * k + rank] = se; }
+  }
+  if (n_valid) atomicAdd(&s_nvalid, n_valid);
+  __syncthreads();
+  // padding: ranks >= number of valid entries
+  for (int r = s_nvalid + threadIdx.x; r < k; r += blockDim.x) { out_id[int64_t(u) * k + r] = -1; out_score[int64_t(u) * k + r] = -CUDART_INF_F; }
+}
+
+// Exact per-user top-k (CUDA cores, pinned fma chain): one CTA per FLAGGED user streams the whole item range, keeps a
+// running k-th-score threshold and compacts a 384-entry buffer by rank counting.  For the users the tensor-core filter
+// cannot serve (see tc_topk_threshold_kernel); unflagged users' CTAs exit at once.
+__global__ void __launch_bounds__(256)
+topk_user_exact_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
+                       const int* __restrict__ flags, int item_lo, int item_hi, const int64_t* __restrict__ excl_ptr,
+                       const int32_t* __restrict__ excl_idx, int k, int32_t* __restrict__ out_id, float* __restrict__ out_score) {
+  const int u = blockIdx.x;
+  if (!flags[u]) return;
+  extern __shared__ float sp[];            // d floats: the user row
+  __shared__ float bs[384], cs[128];
+  __shared__ int bi[384], ci[128];
+  __shared__ int s_n;
+  __shared__ float s_thr;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) sp[e] = P[int64_t(users[u]) * d + e];
+  if (threadIdx.x == 0) { s_n = 0; s_thr = -CUDART_INF_F; }
+  __syncthreads();
+  const int64_t e0 = excl_ptr[u], e1 = excl_ptr[u + 1];
+  auto compact = [&]() {   // keep the k best of the s_n entries, sorted; threshold = k-th score once k entries exist
+    const int n = s_n;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const float se = bs[e];
+      const int ie = bi[e];
+      int rank = 0;
+      for (int f = 0; f < n; ++f) rank += (bs[f] > se) || (bs[f] == se && bi[f] < ie);
+      if (rank < k) { cs[rank] = se; ci[rank] = ie; }
+    }
+    __syncthreads();
+    const int keep = min(n, k);
+    for (int e = threadIdx.x; e < keep; e += blockDim.x) { bs[e] = cs[e]; bi[e] = ci[e]; }
+    if (threadIdx.x == 0) { s_n = keep; if (keep == k) s_thr = cs[k - 1]; }
+    __syncthreads();
+  };
+  for (int base = item_lo; base < item_hi; base += blockDim.x) {
+    const int item = base + threadIdx.x;
+    if (item < item_hi) {
+      const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(item) * d);
+      float acc = 0.f;
+      for (int e = 0; e < d / 4; ++e) {
+        const float4 b = __ldg(q4 + e);
+        acc = fmaf(sp[4 * e], b.x, acc); acc = fmaf(sp[4 * e + 1], b.y, acc);
+        acc = fmaf(sp[4 * e + 2], b.z, acc); acc = fmaf(sp[4 * e + 3], b.w, acc);
+      }
+      if (acc >= s_thr) {
+        int64_t lo = e0, hi = e1;
+        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (excl_idx[m] < item) lo = m + 1; else hi = m; }
+        if (!(lo < e1 && excl_idx[lo] == item)) {
+          const int slot = atomicAdd(&s_n, 1);     // <= 128 kept + 256 new
+          bs[slot] = acc; bi[slot] = item;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_n > 128) compact(); else __syncthreads();
+  }
+  compact();
+  const int n = s_n;
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    out_id[int64_t(u) * k + r] = r < n ? bi[r] : -1;
+    out_score[int64_t(u) * k + r] = r < n ? bs[r] : -CUDART_INF_F;
+  }
+}
+
+// One CTA per SM (TMEM + shared memory): the item tiles are split over `splits` CTAs per user tile so that the CTAs fill
+// whole waves of SMs, with as few splits as reach >= 92 % wave efficiency and >= 8 item tiles per CTA (amortises the A
+// image and the pipeline fill).  top-k: every (user, CTA) contributes TC_GROUPS_PER_CTA group maxima and the threshold
+// needs well over k_top + |excl(u)| of them per user, so splits >= (k_top + 64) / 16 (fewer tiles per CTA are accepted).
+struct TcSplit { int splits, per; };
+static TcSplit tc_pick_splits(int n_utiles, int n_itiles, int k_top, int sms) {
+  int lo = 1, max_splits = std::max(1, std::min(n_itiles / 8, 512));
+  if (k_top > 0) {
+    lo = std::min(n_itiles, (k_top + 64 + 15) / 16);
+    max_splits = std::max(lo, std::min(n_itiles, 512));
+  }
+  int splits = lo;
+  double best = -1.0;
+  for (int sp = lo; sp <= max_splits; ++sp) {
+    const int64_t ctas = int64_t(n_utiles) * sp;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double eff = double(ctas) / double(waves * sms);
+    if (eff > best + 1e-9) { best = eff; splits = sp; }
+    if (eff >= 0.92) { splits = sp; break; }
+  }
+  TcSplit r;
+  r.per = (n_itiles + splits - 1) / splits;
+  r.splits = (n_itiles + r.per - 1) / r.per;
+  return r;
+}
+
+// capacity of the (user, item) list the GEMM kernels fill, in pairs: the ambiguous pairs of the counting pass (~0.1-0.2 %
+// of all pairs) and, for the top-k, the pass-B candidates (about k_top + |excl(u)| per user)
+static inline int64_t tc_list_cap(int n_users, int n_items, int k_top) {
+  return std::min<int64_t>(int64_t(n_users) * std::max(std::max(256, n_items / 256), 8 * k_top), 0x7fffff00);
+}
+
+// Workspace layout.  The item-operand image comes FIRST, at an offset that does not depend on the number of users, so
+// that consecutive calls over user tiles of any size find it in the same place (apr_eval_fullrank_tc_topk's image cache).
+struct TcWs {
+  int64_t off_bimg, off_qmax, off_spos, off_scale, off_aimg, off_amb, off_cnt, off_gmax, off_tau, off_flag, off_ucount,
+      off_ubuf_s, off_ubuf_i, total;
+  int n_utiles, n_itiles;
+  TcSplit split;
+};
+static TcWs tc_ws(int n_users, int n_items, int d, int k_top) {
   const TcLayout L = tc_layout(d);
   TcWs w;
   w.n_utiles = (n_users + TC_BM - 1) / TC_BM;
   w.n_itiles = (n_items + TC_BN - 1) / TC_BN;
+  w.split = tc_pick_splits(w.n_utiles, w.n_itiles, k_top, sm_count());
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o += (bytes + 1023) & ~int64_t(1023); return r; };
+  w.off_bimg = take(int64_t(w.n_itiles) * L.tile_bytes);
+  w.off_qmax = take(16);
   w.off_spos = take(int64_t(n_users) * 4);
   w.off_scale = take(int64_t(n_users) * 4);
   w.off_aimg = take(int64_t(w.n_utiles) * L.tile_bytes);
-  w.off_bimg = take(int64_t(w.n_itiles) * L.tile_bytes);
-  w.off_amb = take(tc_amb_cap(n_users, n_items) * 8);
+  w.off_amb = take(tc_list_cap(n_users, n_items, k_top) * 8);
   w.off_cnt = take(4 * 65536 + 16);  // per-CTA counters
+  w.off_gmax = take(k_top > 0 ? int64_t(n_users) * TC_GROUPS_PER_CTA * w.split.splits * 4 : 0);
+  w.off_tau = take(k_top > 0 ? int64_t(n_users) * 4 : 0);
+  w.off_flag = take(k_top > 0 ? int64_t(n_users) * 4 : 0);
+  w.off_ucount = take(k_top > 0 ? int64_t(n_users) * 4 : 0);
+  w.off_ubuf_s = take(k_top > 0 ? int64_t(n_users) * TOPK_UCAP * 4 : 0);
+  w.off_ubuf_i = take(k_top > 0 ? int64_t(n_users) * TOPK_UCAP * 4 : 0);
   w.total = o;
   return w;
 }
@@ -577,20 +898,27 @@ int apr_eval_tc_timing(int32_t enable, float* gemm_ms_out) {
 
 int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d) {
   if (n_users < 1 || n_items < 1 || !valid_dim(d) || (d % 8) != 0 || d > 256) return -1;
-  return tc_ws(n_users, n_items, d).total;
+  return tc_ws(n_users, n_items, d, 0).total;
 }
 
-int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
-                         int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
-                         const int32_t* excl_idx, int32_t* position, void* ws, int64_t ws_bytes, int32_t* err_flag,
-                         apr_stream_t stream) {
-  if (!P || !Q || !users || !test_item || !excl_ptr || !position || !ws || !err_flag) return APR_E_ARG;
-  if (n_users < 1 || item_hi <= item_lo || item_lo < 0 || !valid_dim(d)) return APR_E_ARG;
+int64_t apr_eval_tc_topk_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t k_top) {
+  if (n_users < 1 || n_items < 1 || !valid_dim(d) || (d % 8) != 0 || d > 256 || k_top < 0 || k_top > 128) return -1;
+  return tc_ws(n_users, n_items, d, k_top).total;
+}
+
+int apr_eval_fullrank_tc_topk(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                              int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                              const int32_t* excl_idx, int32_t k_top, int32_t* position, int32_t* topk_ids,
+                              float* topk_scores, uint64_t q_version, const float* spos_in, void* ws, int64_t ws_bytes,
+                              int32_t* err_flag, apr_stream_t stream) {
+  if (!P || !Q || !users || (!test_item && !spos_in) || !excl_ptr || !position || !ws || !err_flag) return APR_E_ARG;
+  if (n_users < 1 || item_hi <= item_lo || item_lo < 0 || !valid_dim(d) || k_top < 0 || k_top > 128) return APR_E_ARG;
+  if (k_top > 0 && (!topk_ids || !topk_scores || !excl_idx)) return APR_E_ARG;
   if ((d % 8) != 0 || d > 256) return APR_E_UNSUPPORTED;
   if (!aligned16(P) || !aligned16(Q) || (reinterpret_cast<uintptr_t>(ws) & 1023u)) return APR_E_ALIGN;
   const int n_items = item_hi - item_lo;
   const TcLayout L = tc_layout(d);
-  const TcWs W = tc_ws(n_users, n_items, d);
+  const TcWs W = tc_ws(n_users, n_items, d, k_top);
   if (ws_bytes < W.total) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceContext* ctx = device_context();
@@ -601,9 +929,10 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   float* uscale = reinterpret_cast<float*>(base + W.off_scale);
   unsigned char* a_img = reinterpret_cast<unsigned char*>(base + W.off_aimg);
   unsigned char* b_img = reinterpret_cast<unsigned char*>(base + W.off_bimg);
+  float* qmax_all = reinterpret_cast<float*>(base + W.off_qmax);
   int2* amb = reinterpret_cast<int2*>(base + W.off_amb);
   int* amb_count = reinterpret_cast<int*>(base + W.off_cnt);
-  const int amb_cap = int(tc_amb_cap(n_users, n_items));
+  const int64_t list_cap = tc_list_cap(n_users, n_items, k_top);
   // |s_tc - s_chain| <= gamma ||p|| ||q||, every term a worst case (Cauchy-Schwarz: sum |a_k b_k| <= ||p|| ||q||):
   //   split     a = hi + lo + r with |r| <= 2^-18 |a| (two round-to-nearest bf16 steps, x - hi is exact in fp32); the
   //             GEMM keeps hi*hi + hi*lo + lo*hi and drops lo*lo + r_a b + a r_b            <= 3 * 2^-18 * 1.01
@@ -615,7 +944,8 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   auto grid_for = [&](int64_t n) { return int(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, int64_t(sms) * 16))); };
 
   APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, 4 * 65536 + 16, st));
-  { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
+  if (spos_in) APR_CUDA_CHECK(cudaMemcpyAsync(spos, spos_in, size_t(n_users) * 4, cudaMemcpyDeviceToDevice, st));
+  else { int rc = launch_score_pairs(P, Q, d, users, test_item, n_users, spos, st); if (rc) return rc; }
   auto prep = [&](const float* T, const int32_t* ids, int lo, int n, int n_tiles, int is_a, unsigned char* img, float* us) {
     const int64_t thr = int64_t(n_tiles) * 128 * (d / 8);
     if (L.split2 && d == 64) tc_prep_split2_kernel<8><<<grid_for(thr), 256, 0, st>>>(T, ids, lo, n, L.tile_bytes, is_a, gamma, img, us);
@@ -625,8 +955,22 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
                                                                                       L.split2, gamma, img, us);
   };
   prep(P, users, 0, n_users, W.n_utiles, 1, a_img, uscale);
-  prep(Q, nullptr, item_lo, n_items, W.n_itiles, 0, b_img, nullptr);
-  tc_norm_max_kernel<<<(W.n_itiles * 4 + 255) / 256, 256, 0, st>>>(b_img, W.n_itiles, L.nchunk, L.tile_bytes);
+  // The item-operand image (bf16 hi/lo split of Q[item_lo:item_hi) + norms) is the same for every user tile: when the
+  // caller vouches for the table through q_version (non-zero, changed whenever Q changes), it is built once per
+  // (Q, range, d, workspace, version) and found again by the calls over the next user tiles.
+  const bool cached = q_version != 0 && ctx->qimg_valid && ctx->qimg_Q == Q && ctx->qimg_ws == b_img && ctx->qimg_lo == item_lo &&
+                      ctx->qimg_hi == item_hi && ctx->qimg_d == d && ctx->qimg_version == q_version;
+  if (!cached) {
+    ctx->qimg_valid = false;
+    APR_CUDA_CHECK(cudaMemsetAsync(qmax_all, 0, 16, st));
+    prep(Q, nullptr, item_lo, n_items, W.n_itiles, 0, b_img, nullptr);
+    tc_norm_max_kernel<<<(W.n_itiles * 4 + 255) / 256, 256, 0, st>>>(b_img, W.n_itiles, L.nchunk, L.tile_bytes,
+                                                                    reinterpret_cast<unsigned*>(qmax_all));
+    if (q_version != 0) {
+      ctx->qimg_valid = true; ctx->qimg_Q = Q; ctx->qimg_ws = b_img; ctx->qimg_lo = item_lo; ctx->qimg_hi = item_hi;
+      ctx->qimg_d = d; ctx->qimg_version = q_version;
+    }
+  }
   APR_LAUNCH_CHECK();
 
   // shared memory: 1024 alignment slack + A image + B stages + (optional) norm ring + barriers
@@ -638,70 +982,124 @@ int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_
   int nstage = int((max_smem - fixed_smem - size_t(norm_slots) * TC_NORM_BYTES) / TC_CHUNK_BYTES);
   nstage = std::max(1, std::min(nstage, 8));
   const size_t smem = fixed_smem + size_t(norm_slots) * TC_NORM_BYTES + size_t(nstage) * TC_CHUNK_BYTES;
-  // one CTA per SM (TMEM + shared memory): split the item tiles so that the CTAs fill whole waves of SMs, with as few
-  // splits as reach >= 92 % wave efficiency and >= 8 item tiles per CTA (amortises the A image and the pipeline fill)
-  int splits = 1;
-  {
-    double best = -1.0;
-    const int max_splits = std::max(1, std::min(W.n_itiles / 8, 512));
-    for (int sp = 1; sp <= max_splits; ++sp) {
-      const int64_t ctas = int64_t(W.n_utiles) * sp;
-      const int64_t waves = (ctas + sms - 1) / sms;
-      const double eff = double(ctas) / double(waves * sms);
-      if (eff > best + 1e-9) { best = eff; splits = sp; }
-      if (eff >= 0.92) { splits = sp; break; }
-    }
-  }
-  const int per = (W.n_itiles + splits - 1) / splits;
-  splits = (W.n_itiles + per - 1) / per;
+  const int splits = W.split.splits, per = W.split.per;
   const int n_ctas = W.n_utiles * splits;
-  if (n_ctas > 65536) return APR_E_UNSUPPORTED;
-  const int cap_cta = int(int64_t(amb_cap) / n_ctas);  // every CTA owns one segment of the list
+  if (n_ctas > (k_top > 0 ? 32768 : 65536)) return APR_E_UNSUPPORTED;   // per-CTA counter block (tile the users)
+  const int cap_cta = int(list_cap / n_ctas);  // every CTA owns one segment of the list
   if (cap_cta < 16) return APR_E_UNSUPPORTED;
   const int32_t meta[2] = {n_ctas, cap_cta};
   APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 65536, meta, 8, cudaMemcpyHostToDevice, st));
+  float* gmax = k_top > 0 ? reinterpret_cast<float*>(base + W.off_gmax) : nullptr;
+  cudaError_t attr_err = cudaSuccess;
+  auto launch_gemm = [&](auto kern, const float* thresholds) {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (attr_err == cudaSuccess)
+      kern<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots,
+                                                               L.split2 ? L.cps : 0, n_users, thresholds, uscale, item_lo,
+                                                               item_hi, W.n_itiles, per, position, amb, amb_count, cap_cta,
+                                                               gmax, err_flag);
+  };
+  const int cps_arg = L.split2 ? L.cps : 0;
+  auto gemm_pass = [&](auto mode_tag, const float* thresholds) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    if (L.nchunk == 4 && cps_arg == 2) launch_gemm(tc_count_kernel<4, 2, MODE>, thresholds);        // d = 128
+    else if (L.nchunk == 8 && cps_arg == 4) launch_gemm(tc_count_kernel<8, 4, MODE>, thresholds);   // d = 256
+    else if (L.nchunk == 2 && cps_arg == 1) launch_gemm(tc_count_kernel<2, 1, MODE>, thresholds);   // d = 64
+    else launch_gemm(tc_count_kernel<0, 0, MODE>, thresholds);
+  };
+  // ---- pass A: position counts (+ group maxima for the top-k) ----
   if (ctx->tc_timing) APR_CUDA_CHECK(cudaEventRecord(ctx->tc_ev[0], st));
-  {
-    cudaError_t attr_err = cudaSuccess;
-    auto launch = [&](auto kern) {
-      attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      if (attr_err == cudaSuccess) kern<<<dim3(W.n_utiles, splits), TC_THREADS, smem, st>>>(a_img, b_img, L.nchunk, L.tile_bytes, nstage, norm_slots, L.split2 ? L.cps : 0, n_users,
-                                                                      spos, uscale, item_lo, item_hi, W.n_itiles, per,
-                                                                      position, amb, amb_count, cap_cta, err_flag);
-    };
-    const int cps_arg = L.split2 ? L.cps : 0;
-    if (L.nchunk == 4 && cps_arg == 2) launch(tc_count_kernel<4, 2>);        // d = 128
-    else if (L.nchunk == 8 && cps_arg == 4) launch(tc_count_kernel<8, 4>);   // d = 256
-    else if (L.nchunk == 2 && cps_arg == 1) launch(tc_count_kernel<2, 1>);   // d = 64
-    else launch(tc_count_kernel<0, 0>);
-    APR_CUDA_CHECK(attr_err);
-  }
+  if (k_top > 0) gemm_pass(std::integral_constant<int, TC_COUNT_GM>(), spos);
+  else gemm_pass(std::integral_constant<int, TC_COUNT>(), spos);
+  APR_CUDA_CHECK(attr_err);
   if (ctx->tc_timing) { APR_CUDA_CHECK(cudaEventRecord(ctx->tc_ev[1], st)); ctx->tc_ev_valid = true; }
   APR_LAUNCH_CHECK();
-  {  // d % 8 == 0 here (checked on entry), so rows are whole float4 pieces
-    const int gx = std::max(1, std::min(8, (sms * 6) / std::max(1, n_ctas)));
-    tc_rescore_group_kernel<<<dim3(gx, n_ctas), 512, 0, st>>>(P, Q, d, users, spos, amb, amb_count, cap_cta, position);
-  }
+  const int gx = std::max(1, std::min(8, (sms * 6) / std::max(1, n_ctas)));
+  // d % 8 == 0 here (checked on entry), so rows are whole float4 pieces
+  tc_rescore_group_kernel<<<dim3(gx, n_ctas), 512, 0, st>>>(P, Q, d, users, spos, amb, amb_count, cap_cta, position);
   APR_LAUNCH_CHECK();
-  return launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st);
+  { int rc = launch_excl_correction(P, Q, d, users, n_users, spos, item_lo, item_hi, excl_ptr, excl_idx, position, st); if (rc) return rc; }
+  if (k_top == 0) return APR_OK;
+
+  // ---- top-k: threshold from the group maxima, pass B collects the candidates, exact re-scoring, selection ----
+  float* tau = reinterpret_cast<float*>(base + W.off_tau);
+  int* flags = reinterpret_cast<int*>(base + W.off_flag);
+  int* ucount = reinterpret_cast<int*>(base + W.off_ucount);
+  float* ubuf_s = reinterpret_cast<float*>(base + W.off_ubuf_s);
+  int32_t* ubuf_i = reinterpret_cast<int32_t*>(base + W.off_ubuf_i);
+  tc_topk_threshold_kernel<<<(n_users * 32 + 255) / 256, 256, 0, st>>>(gmax, TC_GROUPS_PER_CTA * splits, n_users, k_top, excl_ptr,
+                                                                      uscale, qmax_all, tau, flags);
+  APR_LAUNCH_CHECK();
+  // the counting pass's per-CTA fills stay readable (apr_eval_tc_ambiguous) in the upper half of the counter block
+  APR_CUDA_CHECK(cudaMemcpyAsync(amb_count + 32768, amb_count, size_t(std::min(n_ctas, 32768)) * 4, cudaMemcpyDeviceToDevice, st));
+  APR_CUDA_CHECK(cudaMemsetAsync(amb_count, 0, size_t(n_ctas) * 4, st));
+  APR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, size_t(n_users) * 4, st));
+  gemm_pass(std::integral_constant<int, TC_COLLECT>(), tau);
+  APR_CUDA_CHECK(attr_err);
+  APR_LAUNCH_CHECK();
+  tc_topk_rescore_kernel<<<dim3(gx, n_ctas), 512, 0, st>>>(P, Q, d, users, n_users, tau, amb, amb_count, cap_cta, W.n_utiles,
+                                                          excl_ptr, excl_idx, ubuf_s, ubuf_i, ucount, flags);
+  APR_LAUNCH_CHECK();
+  topk_select_kernel<<<n_users, 128, 0, st>>>(ubuf_s, ubuf_i, TOPK_UCAP, ucount, flags, k_top, topk_ids, topk_scores);
+  APR_LAUNCH_CHECK();
+  topk_user_exact_kernel<<<n_users, 256, size_t(d) * 4, st>>>(P, Q, d, users, flags, item_lo, item_hi, excl_ptr, excl_idx, k_top,
+                                                             topk_ids, topk_scores);
+  APR_LAUNCH_CHECK();
+  return APR_OK;
 }
 
-/* number of ambiguous pairs of the last apr_eval_fullrank_tc call on this workspace and the capacity of the list
- * (synchronises the stream); count > capacity means the list overflowed and the result is invalid (exact path). */
-int apr_eval_tc_ambiguous(const void* ws, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
+int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                         int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                         const int32_t* excl_idx, int32_t* position, void* ws, int64_t ws_bytes, int32_t* err_flag,
+                         apr_stream_t stream) {
+  return apr_eval_fullrank_tc_topk(P, Q, d, users, test_item, n_users, item_lo, item_hi, excl_ptr, excl_idx, 0, position,
+                                   nullptr, nullptr, 0, nullptr, ws, ws_bytes, err_flag, stream);
+}
+
+/* Diagnostics of the last call on this workspace (synchronises the stream).  count_host[0] = (user, item) pairs the
+ * counting pass sent to exact re-scoring, count_host[1] = capacity of that list (0: a CTA's segment overflowed and the
+ * positions are invalid -- use the exact path); with k_top > 0 also count_host[2] = pass-B candidates of the top-k,
+ * count_host[3] = users served by the exact per-user kernel instead of the tensor-core filter. */
+int apr_eval_tc_ambiguous(const void* ws, int32_t n_users, int32_t n_items, int32_t d, int32_t k_top, int32_t* count_host,
                           apr_stream_t stream) {
-  if (!ws || !count_host || n_users < 1 || n_items < 1 || !valid_dim(d)) return APR_E_ARG;
-  const TcWs W = tc_ws(n_users, n_items, d);
+  if (!ws || !count_host || n_users < 1 || n_items < 1 || !valid_dim(d) || k_top < 0 || k_top > 128) return APR_E_ARG;
+  const TcWs W = tc_ws(n_users, n_items, d, k_top);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::vector<int32_t> h(65536 + 2);
   APR_CUDA_CHECK(cudaMemcpyAsync(h.data(), static_cast<const char*>(ws) + W.off_cnt, (65536 + 2) * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> fl;
+  if (k_top > 0) {
+    fl.resize(size_t(n_users));
+    APR_CUDA_CHECK(cudaMemcpyAsync(fl.data(), static_cast<const char*>(ws) + W.off_flag, size_t(n_users) * 4, cudaMemcpyDeviceToHost, st));
+  }
   APR_CUDA_CHECK(cudaStreamSynchronize(st));
   const int n_ctas = h[65536], cap_cta = h[65537];
-  int64_t total = 0;
+  int64_t total = 0, total_b = 0;
   bool overflow = false;
-  for (int k = 0; k < n_ctas && k < 65536; ++k) { total += h[k]; overflow |= h[k] > cap_cta; }
+  // k_top > 0: the counting pass's fills were moved to [32768, ...), [0, n_ctas) holds the candidate pass
+  const int off_a = k_top > 0 ? 32768 : 0;
+  for (int k = 0; k < n_ctas && k < 32768; ++k) {
+    total += h[off_a + k];
+    overflow |= h[off_a + k] > cap_cta;
+    if (k_top > 0) total_b += std::min(h[k], cap_cta);
+  }
+  if (k_top == 0) for (int k = 32768; k < n_ctas && k < 65536; ++k) { total += h[k]; overflow |= h[k] > cap_cta; }
   count_host[0] = int32_t(std::min<int64_t>(total, 0x7fffffff));
   count_host[1] = overflow ? 0 : int32_t(std::min<int64_t>(int64_t(cap_cta) * n_ctas, 0x7fffffff));  // 0 => overflow
+  count_host[2] = int32_t(std::min<int64_t>(total_b, 0x7fffffff));
+  int nfb = 0;
+  for (int32_t f : fl) nfb += f != 0;
+  count_host[3] = nfb;
+  return APR_OK;
+}
+
+/* K10: cross-shard merge.  in_ids / in_scores [n_users, m] (m = shards * k entries per user, id < 0 = padding) ->
+ * out_ids / out_scores [n_users, k], the k best by (score desc, id asc), padded with -1 / -inf.  m <= 1024. */
+int apr_topk_merge(const int32_t* in_ids, const float* in_scores, int32_t n_users, int32_t m, int32_t k, int32_t* out_ids,
+                   float* out_scores, apr_stream_t stream) {
+  if (!in_ids || !in_scores || !out_ids || !out_scores || n_users < 1 || m < 1 || m > TOPK_UCAP || k < 1 || k > 128) return APR_E_ARG;
+  topk_select_kernel<<<n_users, 128, 0, static_cast<cudaStream_t>(stream)>>>(in_scores, in_ids, m, nullptr, nullptr, k, out_ids, out_scores);
+  APR_LAUNCH_CHECK();
   return APR_OK;
 }
 

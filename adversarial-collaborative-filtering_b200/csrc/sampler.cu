@@ -12,15 +12,22 @@ __global__ void __launch_bounds__(256)
 sample_epoch_kernel(const int32_t* __restrict__ pairs_u, const int32_t* __restrict__ pairs_i, uint32_t n_pairs,
                     int64_t n_draws, int dns, uint32_t num_items, const int64_t* __restrict__ csr_ptr,
                     const int32_t* __restrict__ csr_idx, int csr_rows, uint32_t seed, uint32_t epoch, PermKeys keys,
-                    int half_bits, int32_t* __restrict__ out_u, int32_t* __restrict__ out_i,
-                    int32_t* __restrict__ out_udns, int32_t* __restrict__ out_j, int32_t* err_flag) {
-  for (int64_t f = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; f < n_draws; f += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t t = f / dns;
-    const int k = int(f - t * dns);
+                    int half_bits, int batch, int batch_lo, int batch_local, int32_t* __restrict__ out_u,
+                    int32_t* __restrict__ out_i, int32_t* __restrict__ out_udns, int32_t* __restrict__ out_j,
+                    int32_t* err_flag) {
+  // a rank of a sharded run draws the triples [batch_lo, batch_lo + batch_local) of every batch: `fl` numbers ITS draws,
+  // `f` is the draw's index in the whole epoch -- the counter of every random number -- so the shards are bit-identical
+  // slices of the unsharded epoch ("counter-based RNG keyed by global triple index; no collective")
+  for (int64_t fl = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; fl < n_draws; fl += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t tl = fl / dns;
+    const int k = int(fl - tl * dns);
+    const int64_t step = tl / batch_local;
+    const int64_t t = step * batch + batch_lo + (tl - step * batch_local);
+    const int64_t f = t * dns + k;
     const uint32_t pair = feistel_perm(uint32_t(t), n_pairs, half_bits, keys);
     const int32_t user = pairs_u[pair];
-    if (k == 0) { out_u[t] = user; out_i[t] = pairs_i[pair]; }
-    out_udns[f] = user;
+    if (k == 0) { out_u[tl] = user; out_i[tl] = pairs_i[pair]; }
+    out_udns[fl] = user;
     int64_t lo = 0, hi = 0;
     if (user < csr_rows) { lo = csr_ptr[user]; hi = csr_ptr[user + 1]; }
     uint32_t w[4];
@@ -38,7 +45,7 @@ sample_epoch_kernel(const int32_t* __restrict__ pairs_u, const int32_t* __restri
       if (!(a < hi && csr_idx[a] == cand)) { chosen = cand; break; }
     }
     if (chosen < 0) { atomicOr(err_flag, 1); chosen = 0; }
-    out_j[f] = chosen;
+    out_j[fl] = chosen;
   }
 }
 
@@ -105,15 +112,17 @@ using namespace apr;
 
 extern "C" {
 
-int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch, int32_t num_items,
-                     const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows, uint32_t seed, uint32_t epoch,
-                     int32_t dns, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
-                     apr_stream_t stream) {
+int apr_sample_epoch_shard(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch,
+                           int32_t num_items, const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows,
+                           uint32_t seed, uint32_t epoch, int32_t dns, int32_t batch_lo, int32_t batch_local,
+                           int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
+                           apr_stream_t stream) {
   if (!pairs_u || !pairs_i || !csr_ptr || !out_u || !out_i || !out_udns || !out_j || !err_flag) return APR_E_ARG;
   if (n_pairs < 1 || n_pairs > 0x7fffffffLL || batch < 1 || num_items < 1 || dns < 1 || csr_rows < 0) return APR_E_ARG;
+  if (batch_lo < 0 || batch_local < 1 || batch_lo + batch_local > batch) return APR_E_ARG;
   const int64_t S = n_pairs / batch;
   if (S < 1) return APR_E_ARG;
-  const int64_t n_draws = S * batch * dns;
+  const int64_t n_draws = S * batch_local * dns;
   PermKeys keys;
   uint32_t a[4], b[4];
   philox4x32_10(0, 0, 0, epoch, seed, kStreamPerm, a);
@@ -126,9 +135,18 @@ int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_p
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sample_epoch_kernel<<<grid_for(n_draws, 256), 256, 0, st>>>(pairs_u, pairs_i, uint32_t(n_pairs), n_draws, dns,
                                                               uint32_t(num_items), csr_ptr, csr_idx, csr_rows, seed, epoch,
-                                                              keys, bits / 2, out_u, out_i, out_udns, out_j, err_flag);
+                                                              keys, bits / 2, batch, batch_lo, batch_local, out_u, out_i,
+                                                              out_udns, out_j, err_flag);
   APR_LAUNCH_CHECK();
   return APR_OK;
+}
+
+int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch, int32_t num_items,
+                     const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows, uint32_t seed, uint32_t epoch,
+                     int32_t dns, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
+                     apr_stream_t stream) {
+  return apr_sample_epoch_shard(pairs_u, pairs_i, n_pairs, batch, num_items, csr_ptr, csr_idx, csr_rows, seed, epoch, dns, 0,
+                                batch, out_u, out_i, out_udns, out_j, err_flag, stream);
 }
 
 int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_dns, const int32_t* j_dns, int64_t n_pos,

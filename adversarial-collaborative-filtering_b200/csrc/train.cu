@@ -1201,8 +1201,8 @@ static int env_int(const char* name, int dflt) {
 // re-instantiated inside the timed region).  A full cache recycles its least recently used graph of the same topology
 // through cudaGraphExecUpdate (parameters only).
 // ------------------------------------------------------------------------------------------------
-constexpr int kGraphGroups[] = {8, 4, 2, 1};
-constexpr size_t kGraphCacheMax = 64;
+constexpr int kGraphGroups[] = {32, 16, 8, 4, 2, 1};
+constexpr size_t kGraphCacheMax = 96;
 
 static GraphEntry* graph_find(DeviceContext& ax, const StepCtx& key, const void* fn, int n) {
   for (auto& g : ax.graphs)
@@ -1313,7 +1313,7 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
     };
     // Graph replay pays off when a step is long enough for the saved dependency latency to matter and the batch is large
     // enough for the three-stream layout (APR_GRAPH=0 switches it off, APR_GRAPH_MIN_BATCH moves the threshold).
-    static const int use_graph = env_int("APR_GRAPH", 1), graph_min_batch = env_int("APR_GRAPH_MIN_BATCH", 32768);
+    static const int use_graph = env_int("APR_GRAPH", 1), graph_min_batch = env_int("APR_GRAPH_MIN_BATCH", 1024);
     if (use_graph && c.B >= graph_min_batch && dyn_dev) {
       StepCtx key = c;                    // static part: everything except the steps and the stats pointer of this call
       key.s_begin = key.s_end = 0;
@@ -1337,8 +1337,12 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
           if (rc) return rc;
         }
       }
-      dyn_set_kernel<<<1, 1, 0, st>>>(const_cast<StepDyn*>(dyn_dev), c.s_begin, c.stats);
-      APR_LAUNCH_CHECK();
+      // the cursor carries over from one sub-chunk of a call to the next (every graph advances it by its own step
+      // count): it is set once, in front of the call's first sub-chunk
+      if (c.s_begin == 0) {
+        dyn_set_kernel<<<1, 1, 0, st>>>(const_cast<StepDyn*>(dyn_dev), 0, c.stats);
+        APR_LAUNCH_CHECK();
+      }
       int left = c.s_end - c.s_begin;
       for (size_t k = 0; k < kNG; ++k) {
         while (left >= kGraphGroups[k]) {

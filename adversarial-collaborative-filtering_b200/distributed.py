@@ -30,63 +30,112 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 1) -> Tuple[int, in
 
 
 def merge_topk(ids: np.ndarray, scores: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
-    """Merge per-shard top-k lists [n_users, world*k] (id -1 = padding) into the global top-k by
-    (score desc, item id asc) -- the order the single-range kernel produces."""
+    """Host statement of the K10 merge (the GPU path uses the ``apr_topk_merge`` kernel): per-shard top-k lists
+    [n_users, world*k] (id -1 = padding) -> the global top-k by (score desc, item id asc), the order the single-range
+    kernel produces.  Vectorised over users."""
     n = ids.shape[0]
-    out_i = np.full((n, k), -1, dtype=np.int32)
-    out_s = np.full((n, k), -np.inf, dtype=np.float32)
-    for u in range(n):
-        ok = ids[u] >= 0
-        ii, ss = ids[u][ok], scores[u][ok]
-        order = np.lexsort((ii, -ss.astype(np.float64)))[:k]
-        out_i[u, :order.size] = ii[order]
-        out_s[u, :order.size] = ss[order]
+    pad = ids < 0
+    key_s = np.where(pad, np.inf, -scores.astype(np.float64))           # padding sorts last
+    order = np.lexsort((ids, key_s), axis=-1)[:, :k]
+    out_i = np.take_along_axis(ids, order, axis=1).astype(np.int32)
+    out_s = np.take_along_axis(scores, order, axis=1).astype(np.float32)
+    gone = np.take_along_axis(pad, order, axis=1)
+    out_i[gone] = -1
+    out_s[gone] = -np.inf
+    if out_i.shape[1] < k:                                             # fewer than k entries per user in total
+        out_i = np.concatenate([out_i, np.full((n, k - out_i.shape[1]), -1, np.int32)], axis=1)
+        out_s = np.concatenate([out_s, np.full((n, k - out_s.shape[1]), -np.inf, np.float32)], axis=1)
     return out_i, out_s
 
 
-def evaluate_item_sharded(eval_range: Callable[[int, int], Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]],
-                          num_items: int, k_top: int = 0, group=None):
-    """Item-sharded full-rank evaluation.
+def _merge_any(ids: torch.Tensor, scores: torch.Tensor, k: int):
+    if ids.is_cuda:
+        from . import engine
+        return engine.topk_merge(ids.contiguous(), scores.contiguous(), k)        # K10 on the GPU
+    mi, ms = merge_topk(ids.numpy(), scores.numpy(), k)
+    return torch.from_numpy(mi), torch.from_numpy(ms)
+
+
+def evaluate_item_sharded(eval_range: Callable, num_items: int, k_top: int = 0, group=None,
+                          held_out_scores: Optional[Callable[[int, int], torch.Tensor]] = None):
+    """Item-sharded full-rank evaluation (utils.py:221-267 over a partitioned catalogue).
 
     ``eval_range(lo, hi)`` -> (position[int32 n], topk_ids[n,k]|None, topk_scores[n,k]|None) for the item range
-    [lo, hi) (``engine.eval_fullrank`` on the GPU path).  Returns the global (position, topk_ids, topk_scores) on every
-    rank; positions are exact sums, the top-k merge reproduces the single-range order."""
+    [lo, hi).  When a rank holds only its shard of the item table it cannot score a held-out item that lives elsewhere:
+    ``held_out_scores(lo, hi)`` then returns, per user, score(u, test_item[u]) if lo <= test_item[u] < hi else 0, ONE
+    all_reduce(sum) makes the exact scores known everywhere (x + 0 == x) and ``eval_range(lo, hi, spos)`` receives
+    them.  Returns the global (position, topk_ids, topk_scores) on every rank: positions are exact sums (second
+    all_reduce), the per-shard top-k lists are all_gathered and merged by (score desc, id asc) -- on the GPU by the
+    ``apr_topk_merge`` kernel."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    lo, hi = shard_bounds(num_items, world, rank, align=64)
-    if hi > lo:
+    lo, hi = shard_bounds(num_items, world, rank, align=128)
+    if hi <= lo:  # more ranks than 128-item blocks: this rank has nothing to score
+        lo = hi = 0
+    if held_out_scores is not None:
+        spos = held_out_scores(lo, hi)
+        if world > 1:
+            dist.all_reduce(spos, op=dist.ReduceOp.SUM, group=group)
+        pos, ids, sc = eval_range(lo, hi, spos)
+    else:
         pos, ids, sc = eval_range(lo, hi)
-    else:  # more ranks than 64-item blocks: this rank has nothing to score
-        pos, ids, sc = eval_range(0, 0)
     if world == 1:
         return pos, ids, sc
     dist.all_reduce(pos, op=dist.ReduceOp.SUM, group=group)
     if not k_top:
         return pos, None, None
-    gi = [torch.empty_like(ids) for _ in range(world)]
-    gs = [torch.empty_like(sc) for _ in range(world)]
-    dist.all_gather(gi, ids, group=group)
-    dist.all_gather(gs, sc, group=group)
-    mi, ms = merge_topk(torch.cat(gi, dim=1).cpu().numpy(), torch.cat(gs, dim=1).cpu().numpy(), k_top)
-    return pos, torch.from_numpy(mi).to(pos.device), torch.from_numpy(ms).to(pos.device)
+    n = ids.shape[0]
+    gi = torch.empty((world * n, k_top), dtype=ids.dtype, device=ids.device)
+    gs = torch.empty((world * n, k_top), dtype=sc.dtype, device=sc.device)
+    dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    dist.all_gather_into_tensor(gs, sc.contiguous(), group=group)
+    gi, gs = gi.view(world, n, k_top), gs.view(world, n, k_top)
+    mi, ms = _merge_any(gi.permute(1, 0, 2).reshape(n, world * k_top), gs.permute(1, 0, 2).reshape(n, world * k_top), k_top)
+    return pos, mi, ms
 
 
-def evaluate_item_sharded_cuda(P, Q, users, test_item, num_items, excl_ptr, excl_idx, k_top=0, group=None):
-    """CUDA front end.  Every rank holds the user rows it evaluates and a replica of Q (10 GB even for config 5:
-    10M x 256 fp32) but SCORES only its item range, so the GEMM work and the top-K selection are sharded G ways."""
+def evaluate_item_sharded_cuda(P, Q, users, test_item, num_items, excl_ptr, excl_idx, k_top=0, group=None,
+                               q_row_offset: Optional[int] = None, exact: bool = False, cache_q: bool = False):
+    """CUDA front end.  ``Q`` is either the whole item table (``q_row_offset`` None) or ONLY this rank's shard: the rows
+    [q_row_offset, q_row_offset + Q.shape[0]) with q_row_offset == shard_bounds(num_items, world, rank, 128)[0], so that
+    a 10M x 256 catalogue costs 10.2 GB / world per GPU.  Every rank holds the user rows it evaluates (``P``; callers with
+    row-sharded user tables all_gather one user tile at a time) and scores them against its item range on the tensor cores
+    (``apr_eval_fullrank_tc_topk``; ``exact`` forces the fp32 CUDA-core kernel, which needs the whole table)."""
     from . import engine
+    n = users.numel()
+    dev = P.device
+    off = 0 if q_row_offset is None else int(q_row_offset)
+    use_tc = (not exact) and engine.tc_supported(P.shape[1])
+    if q_row_offset is not None and not use_tc:
+        raise ValueError("a sharded item table needs the tensor-core path (d % 8 == 0, d <= 256, exact=False)")
 
-    def eval_range(lo, hi):
-        n = users.numel()
+    def empty():
+        z = torch.zeros(n, dtype=torch.int32, device=dev)
+        if k_top:
+            return (z, torch.full((n, k_top), -1, dtype=torch.int32, device=dev),
+                    torch.full((n, k_top), float("-inf"), dtype=torch.float32, device=dev))
+        return z, None, None
+
+    def held_out_scores(lo, hi):
+        # score(u, test_item[u]) where this rank owns the row, 0 elsewhere -- no host synchronisation (masked, not compacted)
         if hi <= lo:
-            z = torch.zeros(n, dtype=torch.int32, device=P.device)
-            if k_top:
-                return (z, torch.full((n, k_top), -1, dtype=torch.int32, device=P.device),
-                        torch.full((n, k_top), float("-inf"), dtype=torch.float32, device=P.device))
-            return z, None, None
-        return engine.eval_fullrank(P, Q, users, test_item, lo, hi, excl_ptr, excl_idx, k_top)
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+        mine = (test_item >= lo) & (test_item < hi)
+        items = torch.where(mine, test_item, torch.full_like(test_item, lo))
+        s = engine.score_pairs(P, Q, users, items, q_row_offset=off)
+        return torch.where(mine, s, torch.zeros_like(s))
 
-    return evaluate_item_sharded(eval_range, num_items, k_top, group)
+    def eval_range(lo, hi, spos=None):
+        if hi <= lo:
+            return empty()
+        if use_tc:
+            r = engine.eval_fullrank_tc(P, Q, users, test_item, lo, hi, excl_ptr, excl_idx, check=False, k_top=k_top,
+                                        cache_q=cache_q, spos=spos, q_row_offset=off)
+            return (r[0], r[1], r[2]) if k_top else (r[0], None, None)
+        return engine.eval_fullrank(P, Q, users, test_item, lo, hi, excl_ptr, excl_idx, k_top, exact=True)
+
+    return evaluate_item_sharded(eval_range, num_items, k_top, group,
+                                 held_out_scores if (q_row_offset is not None) else None)
 
 
 # ---------------------------------------------------------------------------------------------------------

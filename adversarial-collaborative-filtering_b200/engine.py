@@ -57,29 +57,36 @@ def init_truncated_normal(W: torch.Tensor, stddev: float, seed: int, table_id: i
     rows, d = W.shape
     _lib.check(_lib.lib().apr_init_truncated_normal(_ptr(W, torch.float32), rows, d, float(stddev), seed & 0xFFFFFFFF,
                                                     table_id & 0xFFFFFFFF, tag, _stream()))
+    touch(W)
 
 
 def fill(x: torch.Tensor, value: float) -> None:
     _lib.check(_lib.lib().apr_fill_f32(_ptr(x, torch.float32), x.numel(), float(value), _stream()))
+    touch(x)
 
 
 def sample_epoch(pairs_u: torch.Tensor, pairs_i: torch.Tensor, batch: int, num_items: int, csr_ptr: torch.Tensor,
-                 csr_idx: torch.Tensor, seed: int, epoch: int, dns: int = 1):
-    """-> (u[S,B], i[S,B], u_dns[S,B*dns], j[S,B*dns]) int32 device tensors (APR.py:39-81)."""
+                 csr_idx: torch.Tensor, seed: int, epoch: int, dns: int = 1, rank: int = 0, world: int = 1):
+    """-> (u[S,Bl], i[S,Bl], u_dns[S,Bl*dns], j[S,Bl*dns], err) int32 device tensors (APR.py:39-81).
+    ``batch`` is the GLOBAL batch; with world > 1 this rank draws its slice [rank*Bl, (rank+1)*Bl) of every batch,
+    Bl = batch // world -- bit-identical to the same columns of the world == 1 result (no collective)."""
     n = pairs_u.numel()
     S = n // batch
     if S < 1:
         raise ValueError("fewer training pairs than one batch")
+    if batch % world:
+        raise ValueError("the global batch must be a multiple of the number of ranks")
+    bl = batch // world
     dev = pairs_u.device
-    u = torch.empty((S, batch), dtype=torch.int32, device=dev)
-    i = torch.empty((S, batch), dtype=torch.int32, device=dev)
-    ud = torch.empty((S, batch * dns), dtype=torch.int32, device=dev)
-    j = torch.empty((S, batch * dns), dtype=torch.int32, device=dev)
+    u = torch.empty((S, bl), dtype=torch.int32, device=dev)
+    i = torch.empty((S, bl), dtype=torch.int32, device=dev)
+    ud = torch.empty((S, bl * dns), dtype=torch.int32, device=dev)
+    j = torch.empty((S, bl * dns), dtype=torch.int32, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().apr_sample_epoch(_ptr(pairs_u, torch.int32), _ptr(pairs_i, torch.int32), n, batch, num_items,
-                                           _ptr(csr_ptr, torch.int64), _ptr(csr_idx, torch.int32) if csr_idx.numel() else 0,
-                                           csr_ptr.numel() - 1, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, dns, _ptr(u), _ptr(i),
-                                           _ptr(ud), _ptr(j), _ptr(err), _stream()))
+    _lib.check(_lib.lib().apr_sample_epoch_shard(_ptr(pairs_u, torch.int32), _ptr(pairs_i, torch.int32), n, batch, num_items,
+                                                 _ptr(csr_ptr, torch.int64), _ptr(csr_idx, torch.int32) if csr_idx.numel() else 0,
+                                                 csr_ptr.numel() - 1, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, dns, rank * bl, bl,
+                                                 _ptr(u), _ptr(i), _ptr(ud), _ptr(j), _ptr(err), _stream()))
     return u, i, ud, j, err
 
 
@@ -133,6 +140,8 @@ def train_steps(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: Tra
                 stats: Optional[torch.Tensor] = None) -> None:
     """training_batch over u.shape[0] batches (utils.py:106-119), in place on P, Q, accP, accQ."""
     _lib.check(_lib.lib().apr_train_steps(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
+    touch(P)
+    touch(Q)
 
 
 def train_prepare(P, Q, u, i, j, ws: TrainWorkspace) -> None:
@@ -144,6 +153,8 @@ def train_prepare(P, Q, u, i, j, ws: TrainWorkspace) -> None:
 def train_run(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: TrainWorkspace, mode: int = 0,
               stats: Optional[torch.Tensor] = None) -> None:
     _lib.check(_lib.lib().apr_train_run(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
+    touch(P)
+    touch(Q)
 
 
 def train_layout(n_steps: int, batch: int, d: int) -> dict:
@@ -203,11 +214,12 @@ def loss_acc(P, Q, u, i, j) -> torch.Tensor:
     return out
 
 
-def score_pairs(P, Q, users, items) -> torch.Tensor:
+def score_pairs(P, Q, users, items, q_row_offset: int = 0) -> torch.Tensor:
+    """``q_row_offset``: Q holds rows [q_row_offset, ...) of the item table (item-sharded callers)."""
     n = users.numel()
     out = torch.empty(n, dtype=torch.float32, device=P.device)
     if n:
-        _lib.check(_lib.lib().apr_score_pairs(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1],
+        _lib.check(_lib.lib().apr_score_pairs(_ptr(P, torch.float32), _ptr(Q, torch.float32) - q_row_offset * P.shape[1] * 4, P.shape[1],
                                               _ptr(users, torch.int32), _ptr(items, torch.int32), n, _ptr(out), _stream()))
     return out
 
@@ -228,6 +240,11 @@ def eval_fullrank(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, 
     n = users.numel()
     d = P.shape[1]
     dev = P.device
+    if not exact and tc_supported(d) and n >= 1 and item_hi - item_lo >= 1024:
+        # tensor-core route of the same call (apr_eval_fullrank_tc_topk): identical positions / ids
+        r = eval_fullrank_tc(P, Q, users, test_item, item_lo, item_hi, excl_ptr, excl_idx, position=position, check=False,
+                             k_top=k_top)
+        return (r[0], r[1], r[2]) if k_top else (r[0], None, None)
     if position is None:
         position = torch.zeros(n, dtype=torch.int32, device=dev)
     nbytes = _lib.lib().apr_eval_workspace_bytes(n, k_top, d)
@@ -256,38 +273,96 @@ def eval_tc_timing(enable: bool) -> float:
     return float(ms.value)
 
 
+# grow-only evaluation workspace per device: keeping its address stable is what lets the library find the cached
+# item-operand image again on the next user tile (apr_eval_fullrank_tc_topk, q_version)
+_EVAL_WS = {}
+_TABLE_VERSION = {}
+
+
+def _eval_workspace(nbytes: int, dev) -> torch.Tensor:
+    key = str(dev)
+    ws = _EVAL_WS.get(key)
+    if ws is None or ws.numel() < nbytes + 1024:
+        _EVAL_WS.pop(key, None)
+        ws = None
+        torch.cuda.empty_cache()
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        _EVAL_WS[key] = ws
+    return ws
+
+
+def release_eval_workspace() -> None:
+    _EVAL_WS.clear()
+
+
+def touch(t: torch.Tensor) -> None:
+    """Note that the CONTENT of table ``t`` changed through the raw-pointer kernels (torch's own version counter only sees
+    torch ops): invalidates the cached evaluation image of that table."""
+    _TABLE_VERSION[t.data_ptr()] = _TABLE_VERSION.get(t.data_ptr(), 0) + 1
+
+
+def table_version(t: torch.Tensor) -> int:
+    """Non-zero content tag of a table: torch's in-place version counter combined with the library-side write counter."""
+    v = ((int(t._version) + 1) << 24) ^ (_TABLE_VERSION.get(t.data_ptr(), 0) + 1) ^ ((t.data_ptr() >> 8) << 40)
+    return (v & ((1 << 63) - 1)) | 1
+
+
 def eval_fullrank_tc(P, Q, users, test_item, item_lo: int, item_hi: int, excl_ptr, excl_idx,
-                     position: Optional[torch.Tensor] = None, check: bool = True):
-    """Positions through the tcgen05 bf16x3 filter + exact re-scoring (same results as eval_fullrank(exact=True)).
-    -> (position, n_ambiguous).  ``check`` synchronises to verify the pipeline flag and the ambiguous-list capacity."""
+                     position: Optional[torch.Tensor] = None, check: bool = True, k_top: int = 0, cache_q: bool = False,
+                     spos: Optional[torch.Tensor] = None, q_row_offset: int = 0):
+    """Positions (and, with ``k_top``, the top-k ids / scores of the non-excluded items) through the tcgen05 bf16x3
+    filter + exact re-scoring: same results as eval_fullrank(exact=True).
+    -> (position, n_ambiguous) or, with k_top, (position, ids, scores, info).  ``check`` synchronises to verify the
+    pipeline flag and the list capacity.  ``cache_q`` keeps the item-operand image of Q in a persistent workspace
+    across calls (user tiles) until the table changes (``touch`` / any torch in-place op on it).
+    Item-sharded callers hold only the rows [q_row_offset, q_row_offset + Q.shape[0]) of the item table in ``Q`` and
+    pass ``spos`` (score of each user's held-out item, from the rank that owns that row); then ``test_item`` may be None."""
     n = users.numel()
     d = P.shape[1]
     dev = P.device
     if position is None:
         position = torch.zeros(n, dtype=torch.int32, device=dev)
     n_items = item_hi - item_lo
-    nbytes = _lib.lib().apr_eval_tc_workspace_bytes(n, n_items, d)
+    if q_row_offset and (item_lo < q_row_offset or item_hi > q_row_offset + Q.shape[0]):
+        raise ValueError("item range [%d, %d) is outside the local shard of Q" % (item_lo, item_hi))
+    nbytes = _lib.lib().apr_eval_tc_topk_workspace_bytes(n, n_items, d, k_top)
     if nbytes < 0:
-        raise ValueError("tensor-core evaluation needs d % 8 == 0 and d <= 256")
-    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        raise ValueError("tensor-core evaluation needs d % 8 == 0, d <= 256 and k_top <= 128")
+    ws = _eval_workspace(nbytes, dev) if cache_q else torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
     off = (-ws.data_ptr()) % 1024
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     if excl_idx.numel() == 0:
         excl_idx = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().apr_eval_fullrank_tc(_ptr(P, torch.float32), _ptr(Q, torch.float32), d, _ptr(users, torch.int32),
-                                               _ptr(test_item, torch.int32), n, item_lo, item_hi, _ptr(excl_ptr, torch.int64),
-                                               _ptr(excl_idx, torch.int32), _ptr(position, torch.int32), ws.data_ptr() + off,
-                                               nbytes, _ptr(err), _stream()))
-    n_amb = -1
+    ids = torch.empty((n, k_top), dtype=torch.int32, device=dev) if k_top else None
+    sc = torch.empty((n, k_top), dtype=torch.float32, device=dev) if k_top else None
+    _lib.check(_lib.lib().apr_eval_fullrank_tc_topk(
+        _ptr(P, torch.float32), _ptr(Q, torch.float32) - q_row_offset * d * 4, d, _ptr(users, torch.int32),
+        _ptr(test_item, torch.int32), n, item_lo, item_hi, _ptr(excl_ptr, torch.int64), _ptr(excl_idx, torch.int32), k_top,
+        _ptr(position, torch.int32), _ptr(ids), _ptr(sc), table_version(Q) if cache_q else 0, _ptr(spos, torch.float32),
+        ws.data_ptr() + off, nbytes, _ptr(err), _stream()))
+    info = {"ambiguous": -1}
     if check:
-        c = (ctypes.c_int32 * 2)()
-        _lib.check(_lib.lib().apr_eval_tc_ambiguous(ws.data_ptr() + off, n, n_items, d, c, _stream()))
-        n_amb = int(c[0])
+        c = (ctypes.c_int32 * 4)()
+        _lib.check(_lib.lib().apr_eval_tc_ambiguous(ws.data_ptr() + off, n, n_items, d, k_top, c, _stream()))
+        info = {"ambiguous": int(c[0]), "capacity": int(c[1]), "topk_candidates": int(c[2]), "exact_fallback_users": int(c[3])}
         if int(err.item()) != 0:
             raise RuntimeError("tcgen05 evaluation pipeline timed out (error flag set)")
-        if n_amb > int(c[1]):
-            raise RuntimeError("ambiguous list overflow (%d pairs > %d): use the exact path" % (n_amb, int(c[1])))
-    return position, n_amb
+        if int(c[1]) == 0:
+            raise RuntimeError("ambiguous list overflow (%d pairs): use the exact path" % int(c[0]))
+    if k_top:
+        return position, ids, sc, info
+    return position, info["ambiguous"]
+
+
+def topk_merge(ids: torch.Tensor, scores: torch.Tensor, k: int):
+    """K10: [n_users, m] per-shard lists (id < 0 = padding) -> the k best by (score desc, id asc), on the GPU."""
+    n, m = ids.shape
+    out_i = torch.empty((n, k), dtype=torch.int32, device=ids.device)
+    out_s = torch.empty((n, k), dtype=torch.float32, device=ids.device)
+    if n:
+        _lib.check(_lib.lib().apr_topk_merge(_ptr(ids, torch.int32), _ptr(scores, torch.float32), n, m, k, _ptr(out_i),
+                                             _ptr(out_s), _stream()))
+    return out_i, out_s
 
 
 def sum_squares(x: torch.Tensor) -> torch.Tensor:

@@ -324,6 +324,20 @@ def main_sharded(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfgd, "roofline": roofline, "e2e": e2e, "gpu_launches": K * 8 + 5 * len(chunks), "clocks": clocks}   # per step: fast, pair, 3 stages, 3 barriers
+    # ---- second headline metric at N GPUs: item-sharded full-rank evaluation (BASELINE.json configs[4]) ----------
+    if not args.no_eval and args.eval_users > 0:
+        del t, ws
+        torch.cuda.empty_cache()
+        _, tc_peak, _ = peaks()
+        try:
+            ev = {"config5_%d_users_x_10M_items_d256" % args.eval_users:
+                  bench_eval_config5(torch, engine, dev, tc_peak, args.eval_users, world=world, rank=rank)}
+            ku = min(args.eval_users, 1 << 18)
+            ev["config5_top100_%d_users_x_10M_items_d256" % ku] = bench_eval_config5(torch, engine, dev, tc_peak, ku, k_top=100,
+                                                                                     world=world, rank=rank)
+            line["eval"] = ev
+        except Exception as e:  # never lose the training line
+            line["eval"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
     dist.destroy_process_group()
@@ -626,12 +640,94 @@ def bench_sampler(torch, engine, U, I, B, dev, pairs=1 << 26):
             "note": "includes the output allocation of the call; 24 B/triple streamed + random CSR probes (HBM-latency bound)"}
 
 
+def bench_eval_config5(torch, engine, dev, tc_peak, users_total, tile=16384, I=10_000_000, d=256, k_top=0, world=1, rank=0):
+    """BASELINE.json configs[4] as SURVEY 8(d)/(e) ask for it: users_total users (in tiles of one library call each)
+    against all I items, ITEM-SHARDED over `world` ranks: rank r holds only Q[lo_r:hi_r) (I/world rows), scores every user
+    tile against it on the tensor cores, the held-out scores / positions are all_reduced and, with k_top, the per-shard
+    top-k lists are all_gathered and merged by the apr_topk_merge kernel (apr_b200.distributed).  The item-operand
+    image of the shard is built once and reused by every user tile (cache_q).  Timed on the device, max over ranks."""
+    import torch.distributed as dist
+
+    from apr_b200.distributed import evaluate_item_sharded_cuda, shard_bounds
+    lo, hi = shard_bounds(I, world, rank, 128)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2019)                                                    # same users / held-out items on every rank
+    P = torch.randn((users_total, d), device=dev, generator=g) / d ** 0.5
+    test = torch.randint(0, I, (users_total,), device=dev, dtype=torch.int32, generator=g)
+    g.manual_seed(3000 + rank)                                             # this rank's rows of the item table
+    Qs = torch.randn((hi - lo, d), device=dev, generator=g) / d ** 0.5
+    users = torch.arange(tile, device=dev, dtype=torch.int32)
+    ptr = torch.arange(0, tile + 1, device=dev, dtype=torch.int64)         # exclusion = the held-out item
+    pos = torch.zeros(users_total, dtype=torch.int32, device=dev)
+    n_tiles = users_total // tile
+    last = {}
+
+    def call(k):
+        sl = slice(k * tile, (k + 1) * tile)
+        r = evaluate_item_sharded_cuda(P[sl], Qs, users, test[sl], I, ptr, test[sl], k_top=k_top, q_row_offset=lo, cache_q=True)
+        pos[sl] = r[0]
+        last["ids"] = r[1]
+
+    call(0)                                                                 # warm-up: builds the cached item image
+    call(min(1, n_tiles - 1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if world == 1:
+        engine.eval_tc_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms, n_sampled = 0.0, 0
+    e0.record()
+    for k in range(n_tiles):
+        call(k)
+        if world == 1 and k % 8 == 7:                                       # GEMM-kernel time of every 8th tile (counting pass)
+            kms += engine.eval_tc_timing(True)
+            n_sampled += 1
+    e1.record()
+    torch.cuda.synchronize()
+    if world == 1:
+        engine.eval_tc_timing(False)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    passes = 2 if k_top else 1
+    flops_run = 2.0 * users_total * I * 3 * d * passes
+    sus_peak = sustained_tc_peak(tc_peak)
+    res = {"users": users_total, "items": I, "d": d, "user_tile": tile, "k_top": k_top, "n_gpus": world,
+           "items_per_gpu": hi - lo, "ms": ms, "users_per_s": users_total / (ms * 1e-3),
+           "hr10": float((pos < 10).float().mean().item()),
+           "issued_tflops_whole_run_per_gpu": flops_run / world / (ms * 1e-3) / 1e12,
+           "whole_run_frac_of_sustained_peak": flops_run / world / (ms * 1e-3) / 1e12 / sus_peak,
+           "q_image": "built once per table version, reused by every user tile",
+           "note": "issued bf16 flops = 3 x useful (hi*hi + hi*lo + lo*hi split)%s; whole run = operand split of the user "
+                   "tiles, GEMM pass(es), exact re-scoring, exclusion correction%s" %
+                   (", two GEMM passes with k_top" if k_top else "", ", collectives" if world > 1 else "")}
+    if world == 1 and n_sampled and not k_top:
+        k_ms = kms / n_sampled
+        flops_tile = 2.0 * tile * I * 3 * d
+        res["gemm_kernel_ms_per_tile"] = k_ms
+        res["roofline"] = {"bound": "tensor", "achieved": flops_tile / (k_ms * 1e-3) / 1e12, "peak": sus_peak,
+                           "peak_kind": "sustained (long run); burst peak %.1f" % tc_peak, "unit": "TFLOP/s",
+                           "frac": flops_tile / (k_ms * 1e-3) / 1e12 / sus_peak,
+                           "frac_of_burst_peak": flops_tile / (k_ms * 1e-3) / 1e12 / tc_peak,
+                           "whole_run_achieved": flops_run / (ms * 1e-3) / 1e12, "kernel": "tc_count_kernel<8,4,0>", "traffic": None,
+                           "note": "frac = GEMM + counting kernel of sampled tiles (library CUDA events around its launch)"}
+    if k_top and last.get("ids") is not None:
+        res["top1_valid"] = bool((last["ids"][:, 0] >= 0).all().item())
+    del P, Qs
+    engine.release_eval_workspace()
+    torch.cuda.empty_cache()
+    return res
+
+
 def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
     """Full-rank leave-one-out evaluation (second headline metric): users/s with positions for HR@10/NDCG@10.
     Shapes: BASELINE.json configs[2] (yelp-sort shape, d=128) and a tile of configs[4] (10M items, d=256)."""
     out = {}
 
-    def one(U, I, d, tag, exact_too, reps):
+    def one(U, I, d, tag, exact_too, reps, topks=()):
         g = torch.Generator(device=dev)
         g.manual_seed(2019)
         P = torch.randn((U, d), device=dev, generator=g) / d ** 0.5
@@ -689,63 +785,28 @@ def bench_eval(torch, engine, dev, tc_peak, eval_users=1 << 20):
             res["positions_identical"] = bool(torch.equal(pos_tc, pos_e))
             ms_k, _ = timed(lambda: engine.eval_fullrank(*a, 10, exact=True)[0])
             res["exact_fp32_with_top10"] = {"users_per_s": U / (ms_k * 1e-3), "ms": ms_k}
+        for K in topks:
+            # top-K ids on the tensor-core path (counting pass with group maxima -> threshold -> candidate pass -> exact
+            # re-scoring -> selection): two GEMM passes, same ids as the exact kernel (tests/test_gpu_eval_tc.py)
+            ms_t, _ = timed(lambda: engine.eval_fullrank_tc(*a, check=False, k_top=K)[0])
+            _, ids_t, _, info = engine.eval_fullrank_tc(*a, k_top=K)
+            ent = {"users_per_s": U / (ms_t * 1e-3), "ms": ms_t, "candidates_rescored": info["topk_candidates"],
+                   "exact_fallback_users": info["exact_fallback_users"],
+                   "issued_tflops_whole_call": 2 * flops / (ms_t * 1e-3) / 1e12}
+            if exact_too:
+                _, ids_e, _ = engine.eval_fullrank(*a, K, exact=True)
+                ent["ids_identical_to_exact_kernel"] = bool(torch.equal(ids_t, ids_e))
+            res["tensor_core_top%d" % K] = ent
         res["hr10"] = float((pos_tc < 10).float().mean().item())
         out[tag] = res
 
-    one(25677, 25815, 128, "yelp_shape_d128", True, 3)
-    one(4096, 10_000_000, 256, "config5_tile_4096_users_x_10M_items_d256", False, 1)
-
-    def tiled(U_total, tile, I, d, tag):
-        """configs[4] as SURVEY 8(d) asks for it: >= 2^20 users against all 10 M items, in user tiles of one library call
-        each (the ambiguous-pair list of a call is sized by users x items/256, so a call takes a tile of the users)."""
-        g = torch.Generator(device=dev)
-        g.manual_seed(2019)
-        P = torch.randn((U_total, d), device=dev, generator=g) / d ** 0.5
-        Q = torch.randn((I + 1, d), device=dev, generator=g) / d ** 0.5
-        test = torch.randint(0, I, (U_total,), device=dev, dtype=torch.int32, generator=g)
-        users = torch.arange(U_total, device=dev, dtype=torch.int32)
-        ptr = torch.arange(0, tile + 1, device=dev, dtype=torch.int64)     # exclusion = the held-out item
-        pos = torch.zeros(U_total, dtype=torch.int32, device=dev)
-
-        def call(k, check):
-            sl = slice(k * tile, (k + 1) * tile)
-            return engine.eval_fullrank_tc(P, Q, users[sl], test[sl], 0, I, ptr, test[sl], position=pos[sl], check=check)
-
-        _, namb = call(0, True)                                             # warm-up + capacity / error-flag check
-        pos[:tile].zero_()
-        torch.cuda.synchronize()
-        engine.eval_tc_timing(True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kms = 0.0
-        e0.record()
-        for k in range(U_total // tile):
-            call(k, False)
-            kms += engine.eval_tc_timing(True) if k % 8 == 7 else 0.0     # sample the GEMM-kernel time of every 8th tile
-        e1.record()
-        torch.cuda.synchronize()
-        engine.eval_tc_timing(False)
-        ms = e0.elapsed_time(e1)
-        n_sampled = (U_total // tile) // 8
-        k_ms = kms / max(1, n_sampled)
-        flops_tile = 2.0 * tile * I * 3 * d
-        sus_peak = sustained_tc_peak(tc_peak)
-        out[tag] = {"users": U_total, "items": I, "d": d, "user_tile": tile, "ms": ms,
-                    "users_per_s": U_total / (ms * 1e-3), "ambiguous_pairs_first_tile": namb,
-                    "hr10": float((pos < 10).float().mean().item()), "gemm_kernel_ms_per_tile": k_ms,
-                    "roofline": {"bound": "tensor", "achieved": flops_tile / (k_ms * 1e-3) / 1e12 if k_ms > 0 else None,
-                                 "peak": sus_peak, "peak_kind": "sustained (17 s run); burst peak %.1f" % tc_peak,
-                                 "unit": "TFLOP/s",
-                                 "frac": flops_tile / (k_ms * 1e-3) / 1e12 / sus_peak if k_ms > 0 else None,
-                                 "frac_of_burst_peak": flops_tile / (k_ms * 1e-3) / 1e12 / tc_peak if k_ms > 0 else None,
-                                 "whole_run_achieved": 2.0 * U_total * I * 3 * d / (ms * 1e-3) / 1e12,
-                                 "kernel": "tc_count_kernel<8,4>", "traffic": None,
-                                 "note": "issued bf16 flops = 3 x useful; frac = GEMM kernel of sampled tiles (library "
-                                         "CUDA events); whole_run_* = all tiles incl. operand split and exact re-scoring"}}
-        del P, Q
-        torch.cuda.empty_cache()
+    one(25677, 25815, 128, "yelp_shape_d128", True, 3, topks=(10, 100))
+    one(4096, 10_000_000, 256, "config5_tile_4096_users_x_10M_items_d256", False, 1, topks=(100,))
 
     if eval_users > 0:
-        tiled(eval_users, 16384, 10_000_000, 256, "config5_%d_users_x_10M_items_d256" % eval_users)
+        out["config5_%d_users_x_10M_items_d256" % eval_users] = bench_eval_config5(torch, engine, dev, tc_peak, eval_users)
+        ku = min(eval_users, 1 << 18)
+        out["config5_top100_%d_users_x_10M_items_d256" % ku] = bench_eval_config5(torch, engine, dev, tc_peak, ku, k_top=100)
 
     def sampled(U, I, d, C, tag):
         """configs[1] (pinterest shape): He protocol, 99 sampled negatives + the held-out item per user

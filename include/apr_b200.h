@@ -72,6 +72,17 @@ int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_p
                      int32_t dns, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
                      apr_stream_t stream);
 
+/* The same epoch, partitioned over the ranks of a data-parallel run (sampler row): this call draws only the
+ * triples [batch_lo, batch_lo + batch_local) of every batch -- outputs out_u/out_i [S*batch_local], out_udns/out_j
+ * [S*batch_local*dns].  Every random number is keyed by the triple's index in the WHOLE epoch, so the shards are
+ * bit-identical slices of apr_sample_epoch's output and no collective is needed (rank r of G passes
+ * batch_lo = r * batch / G, batch_local = batch / G). */
+int apr_sample_epoch_shard(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch,
+                           int32_t num_items, const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows,
+                           uint32_t seed, uint32_t epoch, int32_t dns, int32_t batch_lo, int32_t batch_local,
+                           int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
+                           apr_stream_t stream);
+
 /* ---- A7 (dns > 1 branch), utils.py:121-139: for each positive keep the best-scored of its dns negatives
  *      (first maximum wins).  u_dns/j_dns are [n_pos*dns]; out_j is [n_pos]. */
 int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_dns, const int32_t* j_dns, int64_t n_pos,
@@ -162,28 +173,59 @@ int apr_eval_candidates(const float* P, const float* Q, int32_t d, const int32_t
  *      position[k] += #(candidates c : score(u,c) >= score(u, test_item[k])), scores in the pinned fma order;
  *      topk (nullable, k_top > 0): the k_top best candidates by (score desc, item id asc) of this item range,
  *      topk_ids/topk_scores [n_users, k_top], padded with id -1 / -inf.  position must be zeroed by the caller
- *      (item-sharded callers sum the shards' counts).  `exact` = 1 forces the fp32 CUDA-core kernel; 0 lets the
- *      library use the tcgen05 bf16x3 filter + exact re-scoring (same results).
- *      The workspace must hold apr_eval_workspace_bytes(n_users, k_top, d) bytes. */
+ *      (item-sharded callers sum the shards' counts).  `exact` = 1 forces the fp32 CUDA-core kernel; with 0 the call
+ *      goes through apr_eval_fullrank_tc_topk (tcgen05 bf16x3 filter + exact re-scoring, same results) whenever d is
+ *      supported there and the workspace is 1024-byte aligned and holds apr_eval_tc_topk_workspace_bytes(n_users,
+ *      item_hi - item_lo, d, k_top) bytes; otherwise the fp32 kernel runs.
+ *      The workspace must hold at least apr_eval_workspace_bytes(n_users, k_top, d) bytes. */
 int64_t apr_eval_workspace_bytes(int32_t n_users, int32_t k_top, int32_t d);
 int apr_eval_fullrank(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
                       int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
                       const int32_t* excl_idx, int32_t k_top, int32_t* position, int32_t* topk_ids, float* topk_scores,
                       int32_t exact, void* workspace, int64_t workspace_bytes, apr_stream_t stream);
 
-/* ---- A10 / K9 on the tensor cores: the same positions as apr_eval_fullrank (k_top = 0), computed by a tcgen05 bf16x3
- *      GEMM with an error-bounded count and exact fp32 re-scoring of the ambiguous candidates (csrc/eval_tc.cu).
+/* ---- A10 / K9 on the tensor cores: the same positions as apr_eval_fullrank, computed by a tcgen05 bf16x3 GEMM with an
+ *      error-bounded count and exact fp32 re-scoring of the ambiguous candidates (csrc/eval_tc.cu).
  *      d % 8 == 0, d <= 256.  workspace: apr_eval_tc_workspace_bytes(n_users, item_hi - item_lo, d) bytes, 1024-byte
- *      aligned.  *err_flag (device int32) is set if a pipeline wait timed out.  apr_eval_tc_ambiguous writes
- *      count_host[0] = (user, item) pairs sent to exact re-scoring, count_host[1] = capacity of that list
- *      (n_users * max(256, n_items/256)); count > capacity means overflow (result invalid: use the exact path). */
+ *      aligned.  *err_flag (device int32) is set if a pipeline wait timed out. */
 int64_t apr_eval_tc_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d);
 int apr_eval_fullrank_tc(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
                          int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
                          const int32_t* excl_idx, int32_t* position, void* workspace, int64_t workspace_bytes,
                          int32_t* err_flag, apr_stream_t stream);
-int apr_eval_tc_ambiguous(const void* workspace, int32_t n_users, int32_t n_items, int32_t d, int32_t* count_host,
-                          apr_stream_t stream);
+
+/* ---- K9 with the top-k fused onto the same tensor-core pipeline (evaluation.py:54-76: heapq.nlargest order, ties to the
+ *      smaller item id; utils.py:244-261).  Positions as above, plus -- k_top in [1, 128] -- topk_ids / topk_scores
+ *      [n_users, k_top]: the k_top best NON-EXCLUDED items of [item_lo, item_hi) by (exact fp32 chain score desc, id asc),
+ *      padded with -1 / -inf; bit-identical to apr_eval_fullrank(exact = 1).  The counting pass also tracks, per user,
+ *      32 x splits maxima of tensor-core scores of distinct items; the (k_top + |excl(u)|)-th largest of them minus the
+ *      error bound is a lower bound tau_u of the user's k-th best exact score; a second pass over the same operand
+ *      images lists every item with s_tc >= tau_u - E, the list is re-scored exactly, excluded items dropped, and the
+ *      k_top best selected per user.  Users the filter cannot serve (fewer maxima than k_top + |excl(u)|, overflowing
+ *      lists, non-finite rows) are ranked by an exact per-user kernel inside the same call.
+ *      q_version: 0 = build the item-operand image (bf16 hi/lo split of Q[item_lo:item_hi)) on every call; non-zero = the
+ *      caller's version tag of the CONTENT of Q -- the image in `workspace` is reused by following calls with the same
+ *      (Q, range, d, workspace, q_version), e.g. over the next user tiles, and rebuilt when the tag changes.
+ *      spos_in (nullable): the held-out items' scores [n_users], computed elsewhere -- the item-sharded caller, whose
+ *      rank holds only Q[item_lo:item_hi) (pass Q = shard base - item_lo * d floats: only rows of the range are
+ *      dereferenced) and gets score(u, test_item[u]) from the rank that owns that row; test_item may then be NULL.
+ *      workspace: apr_eval_tc_topk_workspace_bytes(n_users, n_items, d, k_top) bytes, 1024-byte aligned.
+ *      apr_eval_tc_ambiguous (synchronises): count_host[0] = (user, item) pairs the counting pass re-scored exactly,
+ *      [1] = capacity of that list (0 = a segment overflowed: positions invalid, use exact = 1), [2] = top-k candidates
+ *      re-scored, [3] = users ranked by the exact per-user kernel. */
+int64_t apr_eval_tc_topk_workspace_bytes(int32_t n_users, int32_t n_items, int32_t d, int32_t k_top);
+int apr_eval_fullrank_tc_topk(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* test_item,
+                              int32_t n_users, int32_t item_lo, int32_t item_hi, const int64_t* excl_ptr,
+                              const int32_t* excl_idx, int32_t k_top, int32_t* position, int32_t* topk_ids,
+                              float* topk_scores, uint64_t q_version, const float* spos_in, void* workspace,
+                              int64_t workspace_bytes, int32_t* err_flag, apr_stream_t stream);
+int apr_eval_tc_ambiguous(const void* workspace, int32_t n_users, int32_t n_items, int32_t d, int32_t k_top,
+                          int32_t* count4_host, apr_stream_t stream);
+
+/* ---- K10: merge of per-shard top-k lists (item-sharded evaluation): in_ids / in_scores [n_users, m] with
+ *      m = shards * k <= 1024 entries per user (id < 0 = padding) -> the k best by (score desc, id asc). */
+int apr_topk_merge(const int32_t* in_ids, const float* in_scores, int32_t n_users, int32_t m, int32_t k, int32_t* out_ids,
+                   float* out_scores, apr_stream_t stream);
 
 /* Measurement hook (bench.py): enable != 0 makes every following apr_eval_fullrank_tc record CUDA events around its GEMM +
  * counting kernel on the caller's stream; *gemm_ms_out (may be NULL) receives the duration of the most recent timed call

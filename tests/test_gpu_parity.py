@@ -213,6 +213,30 @@ def test_sampler_bit_exact(cuda_device):
             assert np.array_equal(g.cpu().numpy(), w)
 
 
+def test_sampler_rank_shards_are_slices_of_the_epoch(cuda_device):
+    """SURVEY 8(e) sampler row: rank r of G draws columns [r*B/G, (r+1)*B/G) of every batch; because every random number
+    is keyed by the triple's index in the whole epoch the shards are bit-identical slices of the oracle's epoch."""
+    from apr_b200 import engine
+    rng = np.random.RandomState(12)
+    U, I = 500, 300
+    lists = [sorted(set(rng.randint(0, I, rng.randint(1, 40)).tolist())) for _ in range(U)]
+    pu = np.concatenate([[u] * len(l) for u, l in enumerate(lists)]).astype(np.int32)
+    pi = np.concatenate(lists).astype(np.int32)
+    ptr, idx = O.build_csr(lists)
+    a = [_dev(pu, torch.int32, cuda_device), _dev(pi, torch.int32, cuda_device)]
+    c = [_dev(ptr, torch.int64, cuda_device), _dev(idx, torch.int32, cuda_device)]
+    for B, dns, G in ((512, 1, 4), (96, 3, 8), (64, 1, 2)):
+        want = O.sample_epoch(pu, pi, B, I, ptr, idx, 2019, 5, dns)
+        bl = B // G
+        for r in range(G):
+            got = engine.sample_epoch(*a, B, I, *c, 2019, 5, dns, rank=r, world=G)
+            assert int(got[4].item()) == 0
+            assert np.array_equal(got[0].cpu().numpy(), want[0][:, r * bl:(r + 1) * bl])
+            assert np.array_equal(got[1].cpu().numpy(), want[1][:, r * bl:(r + 1) * bl])
+            assert np.array_equal(got[2].cpu().numpy(), want[2][:, r * bl * dns:(r + 1) * bl * dns])
+            assert np.array_equal(got[3].cpu().numpy(), want[3][:, r * bl * dns:(r + 1) * bl * dns])
+
+
 def test_select_dns_bit_exact(cuda_device):
     from apr_b200 import engine
     rng = np.random.RandomState(4)
