@@ -59,20 +59,42 @@ class Session(object):
             return self.mode
         return 2 if batch <= self.cluster_max_batch else 0
 
-    def train_steps(self, model, U, I, J, adver: bool, stats=None) -> None:
+    def train_steps(self, model, U, I, J, adver, stats=None, check: bool = False) -> None:
         """S steps over the batches U/I/J [S, B].  Device tensors run as they are; HOST batches (CPU tensors or ndarrays,
         pinned or not -- the reference's feed_dict, utils.py:117-119) are streamed: chunk k+1 travels host->device on a
         copy stream while chunk k trains, so the copies hide behind the step kernels."""
         if not (isinstance(U, torch.Tensor) and U.is_cuda):
-            return self._train_steps_host(model, U, I, J, adver, stats)
+            self._train_steps_host(model, U, I, J, adver, stats)
+            if check:
+                self.check(model)
+            return
         S, B = U.shape
         chunk = max(1, min(S, MAX_CHUNK_TRIPLES // max(B, 1)))
         ws = self.workspace(chunk, B, model.embedding_size)
         for s0 in range(0, S, chunk):
             s1 = min(S, s0 + chunk)
-            engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, U[s0:s1], I[s0:s1], J[s0:s1],
-                               model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws,
-                               mode=self.step_mode(B), stats=None if stats is None else stats[s0:s1])
+            self._steps(model, U[s0:s1], I[s0:s1], J[s0:s1], adver, ws, None if stats is None else stats[s0:s1])
+        if check:
+            self.check(model)
+
+    def _steps(self, model, U, I, J, adver, ws, stats) -> None:
+        """One library call.  ``adver``: False/0 = BPR, True/1 = the model's adversarial mode (--adv grad | random),
+        3 = optimizer of the adversarial loss with Delta == 0 (dns > 1 branch, utils.py:121-139)."""
+        a = (model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, U, I, J, model.learning_rate, model.reg,
+             model.reg_adv, model.eps)
+        if int(adver) == 1 and getattr(model, "adv", "grad") == "random":
+            # APR.py:170-177: update_P/update_Q draw a fresh Delta for every batch
+            engine.train_steps_random(*a, ws, model.seed, model.adv_step, stats=stats)
+            model.adv_step += U.shape[0]
+        else:
+            engine.train_steps(*a, int(adver), ws, mode=self.step_mode(U.shape[1]), stats=stats)
+
+    def check(self, model=None) -> None:
+        """Raise if an id outside its table reached the step (the reference's embedding_lookup raises InvalidArgument);
+        synchronises."""
+        if self._ws is not None and engine.train_status(self._ws) & 1:
+            raise IndexError("a user / item id outside the embedding tables was fed to training_batch "
+                             "(1-based ids, or a model built without the extra row?)")
 
     def _train_steps_host(self, model, U, I, J, adver: bool, stats=None) -> None:
         host = []
@@ -110,9 +132,7 @@ class Session(object):
                     dev[q, :n].copy_(src, non_blocking=True)
                 st["ready"][b].record(st["copy"])
             cur.wait_event(st["ready"][b])
-            engine.train_steps(model.embedding_P, model.embedding_Q, model.acc_P, model.acc_Q, dev[0, :n], dev[1, :n],
-                               dev[2, :n], model.learning_rate, model.reg, model.reg_adv, model.eps, adver, ws,
-                               mode=self.step_mode(B), stats=None if stats is None else stats[s0:s1])
+            self._steps(model, dev[0, :n], dev[1, :n], dev[2, :n], adver, ws, None if stats is None else stats[s0:s1])
             st["free"][b].record(cur)
 
 
@@ -136,14 +156,15 @@ class MF:
         self.epochs = args.epochs
         self.seed = getattr(args, "seed", SEED)
         self.shuffle_count = 0
+        self.adv_step = 0        # global step counter of the `--adv random` noise (one fresh Delta per update_P/update_Q run)
         self.embedding_P = None
         self.embedding_Q = None
 
     def build_graph(self):
         if self.embedding_size % 4 != 0 or not (4 <= self.embedding_size <= 512):
             raise ValueError("embed_size must be a multiple of 4 in [4, 512]")
-        if self.adver and self.adv != "grad":
-            raise NotImplementedError("--adv random is not built (APR.py:170-177 is shape-inconsistent in APR.py)")
+        if self.adver and self.adv not in ("grad", "random"):
+            raise ValueError("--adv must be 'grad' or 'random' (APR.py:170-191)")
         self.device = engine.require_cuda()
         d = self.embedding_size
         kw = dict(dtype=torch.float32, device=self.device)

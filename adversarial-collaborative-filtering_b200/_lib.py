@@ -95,6 +95,9 @@ _SIGNATURES = {
     "apr_train_workspace_init": (ctypes.c_int, [_P, c_int64, _P]),
     "apr_train_steps": (ctypes.c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, c_int32, c_float,
                                        c_float, c_float, c_float, c_int32, c_int32, _P, c_int64, _P, _P]),
+    "apr_train_steps_random": (ctypes.c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, c_int32,
+                                              c_float, c_float, c_float, c_float, c_uint32, c_uint32, _P, c_int64, _P, _P]),
+    "apr_train_status": (ctypes.c_int, [_P, POINTER(c_int32), _P]),
     "apr_train_prepare": (ctypes.c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int64, c_int64, _P, c_int64, _P]),
     "apr_train_run": (ctypes.c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, c_int32, c_int32, c_float,
                                      c_float, c_float, c_float, c_int32, c_int32, _P, c_int64, _P, _P]),

@@ -52,6 +52,27 @@ __host__ __device__ inline uint32_t fmix32(uint32_t x) {
   return x;
 }
 
+// tf.truncated_normal element `e` of table `table_id` (oracle.truncated_normal): Philox counter (e_lo, e_hi, attempt,
+// table_id), key (seed, tag) -> four Box-Muller normals, the first with |z| <= 2 wins, else the next attempt
+__device__ inline float truncated_normal_elem(uint64_t e, uint32_t seed, uint32_t table_id, uint32_t tag) {
+  const float two_pi = 6.283185307179586f;
+  for (uint32_t attempt = 0;; ++attempt) {
+    uint32_t w[4];
+    philox4x32_10(uint32_t(e), uint32_t(e >> 32), attempt, table_id, seed, tag, w);
+    float uf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) uf[k] = __ull2float_rn((unsigned long long)w[k] + 1ull) * 2.3283064365386963e-10f;
+    float z[4];
+    const float r0 = sqrtf(-2.0f * logf(uf[0])), r1 = sqrtf(-2.0f * logf(uf[2]));
+    z[0] = r0 * cosf(two_pi * uf[1]); z[1] = r0 * sinf(two_pi * uf[1]);
+    z[2] = r1 * cosf(two_pi * uf[3]); z[3] = r1 * sinf(two_pi * uf[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (fabsf(z[k]) <= 2.0f) return z[k];
+  }
+}
+constexpr uint32_t kStreamAdv = 0x41445631u;   // --adv random noise (engine.STREAM_ADV)
+
 struct PermKeys { uint32_t k[8]; };
 
 __host__ __device__ inline uint32_t feistel_perm(uint32_t x, uint32_t n, int half_bits, const PermKeys& keys) {

@@ -73,27 +73,8 @@ select_dns_kernel(const float* __restrict__ P, const float* __restrict__ Q, int 
 
 __global__ void __launch_bounds__(256)
 truncated_normal_kernel(float* __restrict__ W, int64_t n, float stddev, uint32_t seed, uint32_t table_id, uint32_t tag) {
-  const float two_pi = 6.283185307179586f;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x) {
-    float val = 0.f;
-    for (uint32_t attempt = 0;; ++attempt) {
-      uint32_t w[4];
-      philox4x32_10(uint32_t(uint64_t(e)), uint32_t(uint64_t(e) >> 32), attempt, table_id, seed, tag, w);
-      float uf[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) uf[k] = __ull2float_rn((unsigned long long)w[k] + 1ull) * 2.3283064365386963e-10f;
-      float z[4];
-      const float r0 = sqrtf(-2.0f * logf(uf[0])), r1 = sqrtf(-2.0f * logf(uf[2]));
-      z[0] = r0 * cosf(two_pi * uf[1]); z[1] = r0 * sinf(two_pi * uf[1]);
-      z[2] = r1 * cosf(two_pi * uf[3]); z[3] = r1 * sinf(two_pi * uf[3]);
-      bool found = false;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (!found && fabsf(z[k]) <= 2.0f) { val = z[k]; found = true; }
-      if (found) break;
-    }
-    W[e] = val * stddev;
-  }
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x)
+    W[e] = truncated_normal_elem(uint64_t(e), seed, table_id, tag) * stddev;
 }
 
 __global__ void fill_kernel(float* __restrict__ x, int64_t n, float v) {

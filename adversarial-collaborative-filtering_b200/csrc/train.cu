@@ -473,6 +473,10 @@ struct StepCtx {
   int nranks, rank, rshift;
   int d, B, S;
   float lr, kreg, reg_adv, eps;
+  float plain_scale;   // factor on the plain data term of a NON-adversarial step: 1, or 1 + reg_adv for the reference's
+                       // dns > 1 branch on an adversarial graph (utils.py:121-139: optimizer on opt_loss with Delta == 0)
+  uint32_t noise_seed, noise_step0;   // --adv random: Philox key / first global step of this call (random_step_kernel)
+  const int* abort;    // nullable: a cross-rank barrier timed out (sharded path) -> every later kernel of the call is a no-op
   int adver;
   const int32_t* ucnt; const int32_t* icnt; const int32_t* nslow;
   const int32_t* npair;   // nullable: pair work units per step (segments [nslow, nslow + 2 npair) are theirs)
@@ -717,7 +721,7 @@ __device__ __forceinline__ void fast_segment(const StepCtx& c, const int user, c
   float r;
   const float cf = bpr_coeff(x, r);
   if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
-  float A = cf, Bc = c.kreg, Cc = 0.f;
+  float A = cf * c.plain_scale, Bc = c.kreg, Cc = 0.f;
   if (c.adver) {
     const float a = c.eps * cf * rsqrt_fast(fmaxf(cf * cf * s_dd, 1e-12f));
     const float b = c.eps * cf * rsqrt_fast(fmaxf(cf * cf * s_pp, 1e-12f));
@@ -817,15 +821,16 @@ __device__ __forceinline__ void segment_complete(const StepCtx& c, const int4 h0
     float r;
     const float cf = bpr_coeff(x, r);
     if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+    const float cs = adver ? cf : cf * c.plain_scale;
 #pragma unroll
-    for (int k = 0; k < V; ++k) g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]);
+    for (int k = 0; k < V; ++k) g.v[k] = f4_fma(cs, f4_sub(q.v[k], n.v[k]), g.v[k]);
     if (!adver) {
       Row<G, V> hi, hj;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
-        hi.v[k] = f4_fma(c.kreg, q.v[k], f4_scale(p.v[k], cf));
-        hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(p.v[k], -cf));
+        hi.v[k] = f4_fma(c.kreg, q.v[k], f4_scale(p.v[k], cs));
+        hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(p.v[k], -cs));
       }
       item_sink<G, V>(c, rc.x, rc.z, q, hi, lane, d);
       item_sink<G, V>(c, rc.y, rc.w, n, hj, lane, d);
@@ -966,7 +971,8 @@ __device__ __forceinline__ void pair_unit(const StepCtx& c, const int4 ph, const
   const float xa = row_dot<G, V>(pa, qa, mask) - row_dot<G, V>(pa, na, mask);
   const float xb = row_dot<G, V>(pb, qb, mask) - row_dot<G, V>(pb, nb, mask);
   float r0, r1;
-  const float ca = bpr_coeff(xa, r0), cb = bpr_coeff(xb, r1);
+  const float ps = c.adver ? 1.0f : c.plain_scale;
+  const float ca = ps * bpr_coeff(xa, r0), cb = ps * bpr_coeff(xb, r1);
   if (st.on) {
     st.loss += softplus_neg(r0) + softplus_neg(r1);
     st.correct += ((xa > 0.f) ? 1.f : 0.f) + ((xb > 0.f) ? 1.f : 0.f);
@@ -1119,6 +1125,7 @@ __global__ void __launch_bounds__(kThreads) general_stage_kernel(StepCtx c, int 
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
+  if (c.abort && *c.abort) return;
   APR_STEP_ARGS(c, s_param)
   if (stage == 0 && !(c.adver && c.icnt[s] > 0)) return;
   general_stage<G, V>(c, s, stage, gid, ngroups, lane, group_mask<G>(), st);
@@ -1131,6 +1138,7 @@ __global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fas
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
+  if (c.abort && *c.abort) return;
   APR_STEP_ARGS(c, s_param)
   fast_range<G, V, FULL>(c, s, c.nslow[s] + (c.npair ? 2 * c.npair[s] : 0), c.ucnt[s], gid, ngroups, lane, group_mask<G>(), st);
   if (stats) stats_flush(stats, s, st.loss, st.correct, lane == 0);
@@ -1142,9 +1150,177 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(StepCtx c, int s_para
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
+  if (c.abort && *c.abort) return;
   APR_STEP_ARGS(c, s_param)
   pair_range<G, V>(c, s, gid, ngroups, lane, group_mask<G>(), st);
   if (stats) stats_flush(stats, s, st.loss, st.correct, lane == 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// --adv random (APR.py:170-177; shape-consistent form evaluation_adv.py:182-189): at every step
+//     Delta_P = eps * l2_normalize(truncated_normal([rows, d], 0, 0.01)),  Delta_Q likewise,
+// drawn afresh for ALL rows; only the rows a batch touches matter, so the noise of a row is generated where the row is
+// used -- counter-based (Philox: element = row * d + column, table id = 2 * global_step + {0: P, 1: Q}, key = (seed,
+// STREAM_ADV)), never a table.  Delta does not depend on the batch, so there is no plain stage: one kernel does every
+// segment and pair (forward, perturbed forward, total gradient, Adagrad; shared items RED into H_Q), then stage 2.
+// ---------------------------------------------------------------------------------------------------------
+template <int G, int V>
+__device__ __forceinline__ void noise_delta(Row<G, V>& dl, const StepCtx& c, uint32_t table_id, int row, int lane,
+                                            unsigned mask) {
+  const int d = c.d;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int e = (k * G + lane) * 4;
+    float4 z = f4_zero();
+    if (e < d) {
+      const uint64_t base = uint64_t(row) * uint64_t(d) + uint64_t(e);
+      z.x = truncated_normal_elem(base, c.noise_seed, table_id, kStreamAdv) * 0.01f;
+      z.y = truncated_normal_elem(base + 1, c.noise_seed, table_id, kStreamAdv) * 0.01f;
+      z.z = truncated_normal_elem(base + 2, c.noise_seed, table_id, kStreamAdv) * 0.01f;
+      z.w = truncated_normal_elem(base + 3, c.noise_seed, table_id, kStreamAdv) * 0.01f;
+    }
+    dl.v[k] = z;
+  }
+  const float sc = delta_scale<G, V>(dl, c.eps, mask);
+#pragma unroll
+  for (int k = 0; k < V; ++k) dl.v[k] = f4_scale(dl.v[k], sc);
+}
+
+// one triple: plain + perturbed forward, adds the user-row gradient into g, returns the item-row gradients hi / hj
+template <int G, int V>
+__device__ __forceinline__ void random_triple(const StepCtx& c, uint32_t tq, const int4 rc, const Row<G, V>& p,
+                                              const Row<G, V>& pd, const Row<G, V>& q, const Row<G, V>& n, Row<G, V>& g,
+                                              Row<G, V>& hi, Row<G, V>& hj, int lane, unsigned mask, StepStats& st) {
+  const float x = row_dot<G, V>(p, q, mask) - row_dot<G, V>(p, n, mask);
+  float r;
+  const float cf = bpr_coeff(x, r);
+  if (st.on) { st.loss += softplus_neg(r); st.correct += (x > 0.f) ? 1.f : 0.f; }
+  Row<G, V> qd, nd;
+  noise_delta<G, V>(qd, c, tq, rc.x, lane, mask);
+  noise_delta<G, V>(nd, c, tq, rc.y, lane, mask);
+#pragma unroll
+  for (int k = 0; k < V; ++k) { qd.v[k] = f4_add(q.v[k], qd.v[k]); nd.v[k] = f4_add(n.v[k], nd.v[k]); }
+  const float xa = row_dot<G, V>(pd, qd, mask) - row_dot<G, V>(pd, nd, mask);
+  float ra;
+  const float ca = c.reg_adv * bpr_coeff(xa, ra);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    g.v[k] = f4_fma(cf, f4_sub(q.v[k], n.v[k]), g.v[k]);
+    g.v[k] = f4_fma(ca, f4_sub(qd.v[k], nd.v[k]), g.v[k]);
+    g.v[k] = f4_fma(c.kreg, p.v[k], g.v[k]);
+    const float4 t = f4_fma(ca, pd.v[k], f4_scale(p.v[k], cf));  // c p + reg_adv c' (p + dP)
+    hi.v[k] = f4_fma(c.kreg, q.v[k], t);
+    hj.v[k] = f4_fma(c.kreg, n.v[k], f4_scale(t, -1.f));
+  }
+}
+
+template <int G, int V>
+__device__ __forceinline__ void random_segment(const StepCtx& c, uint32_t tp, const int4 h0, const int4 h1, const int4* rec,
+                                               int lane, unsigned mask, StepStats& st) {
+  const int d = c.d;
+  float* Pu = P_ROW(c, h0.x);
+  Row<G, V> p, pd, g;
+  row_load<G, V>(p, Pu, lane, d);
+  noise_delta<G, V>(pd, c, tp, h0.x, lane, mask);
+#pragma unroll
+  for (int k = 0; k < V; ++k) pd.v[k] = f4_add(p.v[k], pd.v[k]);
+  row_zero<G, V>(g);
+  int4 rc = h1;
+  for (int pos = h0.y; pos < h0.y + h0.z; ++pos) {
+    if (pos > h0.y) rc = rec[pos];
+    Row<G, V> q, n, hi, hj;
+    row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
+    row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
+    random_triple<G, V>(c, tp + 1u, rc, p, pd, q, n, g, hi, hj, lane, mask, st);
+    item_sink<G, V>(c, rc.x, rc.z, q, hi, lane, d);
+    item_sink<G, V>(c, rc.y, rc.w, n, hj, lane, d);
+  }
+  adagrad_row<G, V>(Pu, AP_ROW(c, h0.x), p, g, lane, d, c.lr);
+}
+
+// pair work unit (two single-triple segments coupled by one item that occurs in both and nowhere else; its workspace
+// slot is struck from stage 2): the shared item's total gradient is the sum of its two occurrences, in registers
+template <int G, int V>
+__device__ __forceinline__ void random_pair(const StepCtx& c, uint32_t tp, const int4 ph, const int4 ra, const int4 rb,
+                                            int lane, unsigned mask, StepStats& st) {
+  const int d = c.d;
+  const bool sa = ra.z == ph.z, sb = rb.z == ph.z;   // the shared item is the POSITIVE of a / of b (else the negative)
+  Row<G, V> pa, pb, qa, na, qb, nb, pda, pdb, ga, gb, hia, hja, hib, hjb;
+  row_load<G, V>(pa, P_ROW(c, ph.x), lane, d);
+  row_load<G, V>(pb, P_ROW(c, ph.y), lane, d);
+  row_load<G, V>(qa, Q_ROW(c, ra.x), lane, d);
+  row_load<G, V>(na, Q_ROW(c, ra.y), lane, d);
+  row_load<G, V>(qb, Q_ROW(c, rb.x), lane, d);
+  row_load<G, V>(nb, Q_ROW(c, rb.y), lane, d);
+  noise_delta<G, V>(pda, c, tp, ph.x, lane, mask);
+  noise_delta<G, V>(pdb, c, tp, ph.y, lane, mask);
+#pragma unroll
+  for (int k = 0; k < V; ++k) { pda.v[k] = f4_add(pa.v[k], pda.v[k]); pdb.v[k] = f4_add(pb.v[k], pdb.v[k]); }
+  row_zero<G, V>(ga);
+  row_zero<G, V>(gb);
+  random_triple<G, V>(c, tp + 1u, ra, pa, pda, qa, na, ga, hia, hja, lane, mask, st);
+  random_triple<G, V>(c, tp + 1u, rb, pb, pdb, qb, nb, gb, hib, hjb, lane, mask, st);
+  Row<G, V> hs;
+#pragma unroll
+  for (int k = 0; k < V; ++k) hs.v[k] = f4_add(sa ? hia.v[k] : hja.v[k], sb ? hib.v[k] : hjb.v[k]);
+  adagrad_row<G, V>(P_ROW(c, ph.x), AP_ROW(c, ph.x), pa, ga, lane, d, c.lr);
+  adagrad_row<G, V>(P_ROW(c, ph.y), AP_ROW(c, ph.y), pb, gb, lane, d, c.lr);
+  const int item_s = sa ? ra.x : ra.y, item_oa = sa ? ra.y : ra.x, item_ob = sb ? rb.y : rb.x;
+  adagrad_row<G, V>(Q_ROW(c, item_oa), AQ_ROW(c, item_oa), sa ? na : qa, sa ? hja : hia, lane, d, c.lr);
+  adagrad_row<G, V>(Q_ROW(c, item_ob), AQ_ROW(c, item_ob), sb ? nb : qb, sb ? hjb : hib, lane, d, c.lr);
+  adagrad_row<G, V>(Q_ROW(c, item_s), AQ_ROW(c, item_s), sa ? qa : na, hs, lane, d, c.lr);
+}
+
+template <int G, int V>
+__global__ void __launch_bounds__(kThreads) random_step_kernel(StepCtx c, int s) {
+  const int lane = threadIdx.x % G;
+  const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
+  const int ngroups = gridDim.x * (kThreads / G);
+  const unsigned mask = group_mask<G>();
+  StepStats st = {0.f, 0.f, c.stats != nullptr};
+  const uint32_t tp = (c.noise_step0 + uint32_t(s)) << 1;          // table id of Delta_P at this step; Delta_Q: tp + 1
+  const int ng = c.nslow[s], np = c.npair ? c.npair[s] : 0, nu = c.ucnt[s];
+  const int first_fast = ng + 2 * np;
+  const int n_seg = ng + (nu - first_fast);
+  const int4* seg_hdr = c.seg_hdr + int64_t(s) * c.B * 2;
+  const int4* rec = c.rec + int64_t(s) * c.B;
+  const int4* pairs = c.pairs + int64_t(s) * (c.B / 2 + 1) * 3;
+  for (int w = gid; w < n_seg + np; w += ngroups) {
+    if (w < n_seg) {
+      const int k = w < ng ? w : first_fast + (w - ng);
+      random_segment<G, V>(c, tp, __ldg(&seg_hdr[2 * k]), __ldg(&seg_hdr[2 * k + 1]), rec, lane, mask, st);
+    } else {
+      if constexpr (V == 1) {
+        const int k = w - n_seg;
+        random_pair<G, V>(c, tp, __ldg(&pairs[3 * k]), __ldg(&pairs[3 * k + 1]), __ldg(&pairs[3 * k + 2]), lane, mask, st);
+      }
+    }
+  }
+  if (c.stats) stats_flush(c.stats, s, st.loss, st.correct, lane == 0);
+}
+
+template <int G, int V>
+static int run_random_steps(const StepCtx& c, cudaStream_t st) {
+  const int gpb = kThreads / G;
+  const int grid = std::max(1, std::min((c.B + gpb - 1) / gpb, sm_count() * 4));
+  const int grid_gen = std::max(1, std::min((c.B + gpb - 1) / gpb, sm_count() * 2));
+  for (int s = c.s_begin; s < c.s_end; ++s) {
+    random_step_kernel<G, V><<<grid, kThreads, 0, st>>>(c, s);
+    general_stage_kernel<G, V><<<grid_gen, kThreads, 0, st>>>(c, s, 2);   // Adagrad on the shared item rows
+  }
+  APR_LAUNCH_CHECK();
+  return APR_OK;
+}
+
+static int dispatch_random_steps(const StepCtx& c, cudaStream_t st) {
+  const int q = c.d / 4;
+  if (q <= 4) return run_random_steps<4, 1>(c, st);
+  if (q <= 8) return run_random_steps<8, 1>(c, st);
+  if (q <= 16) return run_random_steps<16, 1>(c, st);
+  if (q <= 32) return run_random_steps<32, 1>(c, st);
+  if (q <= 64) return run_random_steps<32, 2>(c, st);
+  if (q <= 96) return run_random_steps<32, 3>(c, st);
+  return run_random_steps<32, 4>(c, st);
 }
 
 // device-side step cursor of the replayed graphs (StepDyn): set before the first graph launch of a call, advanced by the
@@ -1572,8 +1748,10 @@ int apr_train_prepare(const int32_t* u, const int32_t* i, const int32_t* j, int3
 
 static int check_train_args(const float* P, const float* Q, const float* accP, const float* accQ, int64_t rows_p,
                             int64_t rows_q, int d, const int32_t* u, const int32_t* i, const int32_t* j, int S, int B,
-                            const void* ws) {
+                            const void* ws, int adver) {
   if (!P || !Q || !accP || !accQ || !u || !i || !j || !ws) return APR_E_ARG;
+  if (adver < 0 || adver > 3) return APR_E_ARG;
+  if (adver == 2) return APR_E_UNSUPPORTED;   // --adv random goes through apr_train_steps_random
   if (S < 1 || B < 1 || rows_p < 1 || rows_q < 1 || !valid_dim(d)) return APR_E_ARG;
   if (!aligned16(P) || !aligned16(Q) || !aligned16(accP) || !aligned16(accQ) || !aligned16(ws)) return APR_E_ALIGN;
   return APR_OK;
@@ -1581,7 +1759,7 @@ static int check_train_args(const float* P, const float* Q, const float* accP, c
 
 static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, int32_t S, int32_t B, float lr, float reg,
                      float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, const TrainLayout& L, float* stats,
-                     int s_begin, int s_end, cudaStream_t st) {
+                     int s_begin, int s_end, cudaStream_t st, uint32_t noise_seed = 0, uint32_t noise_step0 = 0) {
   StepCtx c;
   memset(&c, 0, sizeof(c));
   c.Pb[0] = P; c.Qb[0] = Q; c.aPb[0] = accP; c.aQb[0] = accQ;
@@ -1591,7 +1769,11 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.lr = lr;
   // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
   c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
-  c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
+  // adver 3 = the reference's dns > 1 branch on an adversarial graph (utils.py:121-139): the optimizer minimises
+  // L + reg_adv L_adv + 2 reg-terms with Delta == 0 (update_P / update_Q never run there), i.e. a plain step whose data
+  // term is scaled by 1 + reg_adv and whose regulariser is counted twice
+  c.reg_adv = reg_adv; c.eps = eps; c.adver = adver == 1 ? 1 : 0;
+  c.plain_scale = adver == 3 ? 1.0f + reg_adv : 1.0f;
   c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt);
   c.nslow = at<int32_t>(ws, L.off_nslow);
   c.npair = pairs_enabled(d) ? at<int32_t>(ws, L.off_npair) : nullptr;
@@ -1604,6 +1786,10 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = s_begin; c.s_end = s_end;
+  if (adver == 2) {
+    c.noise_seed = noise_seed; c.noise_step0 = noise_step0;
+    return dispatch_random_steps(c, st);
+  }
   return dispatch_steps(c, mode, st, reinterpret_cast<const StepDyn*>(at<char>(ws, L.off_hdr) + kDynOffset));
 }
 
@@ -1611,7 +1797,7 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
                   const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, float lr, float reg,
                   float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, int64_t ws_bytes, float* stats,
                   apr_stream_t stream) {
-  int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws);
+  int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, adver);
   if (rc) return rc;
   if (mode < 0 || mode > 2) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
@@ -1636,7 +1822,7 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
                     const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, float lr, float reg,
                     float reg_adv, float eps, int32_t adver, int32_t mode, void* ws, int64_t ws_bytes, float* stats,
                     apr_stream_t stream) {
-  int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws);
+  int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, adver);
   if (rc) return rc;
   if (mode < 0 || mode > 2) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
@@ -1675,6 +1861,26 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   return APR_OK;
 }
 
+// --adv random (APR.py:170-177): see random_step_kernel.  Steps s = 0..S-1 of this call use the noise of global step
+// noise_step0 + s; the caller advances noise_step0 by S from call to call.
+int apr_train_steps_random(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
+                           const int32_t* u, const int32_t* i, const int32_t* j, int32_t S, int32_t B, float lr, float reg,
+                           float reg_adv, float eps, uint32_t noise_seed, uint32_t noise_step0, void* ws, int64_t ws_bytes,
+                           float* stats, apr_stream_t stream) {
+  int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, 1);
+  if (rc) return rc;
+  const TrainLayout L = make_layout(S, B, d);
+  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceContext* ctx = device_context();
+  if (!ctx) return APR_E_CUDA;
+  std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+  if (stats) APR_CUDA_CHECK(cudaMemsetAsync(stats, 0, size_t(S) * 2 * sizeof(float), st));
+  rc = prepare_impl(u, i, j, S, B, d, rows_p, rows_q, ws, ws_bytes, st);
+  if (rc) return rc;
+  return run_range(P, Q, accP, accQ, d, S, B, lr, reg, reg_adv, eps, 2, 0, ws, L, stats, 0, S, st, noise_seed, noise_step0);
+}
+
 int apr_train_layout(int32_t S, int32_t B, int32_t d, int64_t* out) {  // 13 entries
   if (!out || S < 1 || B < 1 || !valid_dim(d)) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
@@ -1698,11 +1904,13 @@ int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j
   return rc;
 }
 
-int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
-                            float* const* GQb, float* const* HQb, int32_t nranks, int32_t rank, int32_t d, int32_t S,
-                            int32_t B, float lr, float reg, float reg_adv, float eps, int32_t adver, void* ws,
-                            int64_t ws_bytes, float* stats, int32_t step, int32_t stage, apr_stream_t stream) {
+static int stage_sharded_impl(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                              float* const* GQb, float* const* HQb, int32_t nranks, int32_t rank, int32_t d, int32_t S,
+                              int32_t B, float lr, float reg, float reg_adv, float eps, int32_t adver, void* ws,
+                              int64_t ws_bytes, float* stats, int32_t step, int32_t stage, const int* abort_flag,
+                              apr_stream_t stream) {
   if (!Pb || !Qb || !accPb || !accQb || !GQb || !HQb || !ws) return APR_E_ARG;
+  if (adver < 0 || adver > 1) return APR_E_UNSUPPORTED;   // row-sharded tables: BPR and gradient-based APR only
   if (nranks < 1 || nranks > kMaxRanks || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return APR_E_ARG;
   if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 4) return APR_E_ARG;
   const TrainLayout L = make_layout(S, B, d);
@@ -1725,6 +1933,8 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.d = d; c.B = B; c.S = S; c.lr = lr;
   c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
   c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
+  c.plain_scale = 1.0f;
+  c.abort = abort_flag;
   c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt); c.nslow = at<int32_t>(ws, L.off_nslow);
   c.npair = pairs_enabled(d) ? at<int32_t>(ws, L.off_npair) : nullptr; c.pairs = at<int4>(ws, L.off_pairs);
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr); c.rec = at<int4>(ws, L.off_rec); c.iu_item = at<int32_t>(ws, L.off_iu_item);
@@ -1733,6 +1943,14 @@ int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* ac
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = step; c.s_end = step + 1; c.only_stage = stage; c.cluster_sync = 0;
   return dispatch_steps(c, 0, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int apr_train_stage_sharded(float* const* Pb, float* const* Qb, float* const* accPb, float* const* accQb,
+                            float* const* GQb, float* const* HQb, int32_t nranks, int32_t rank, int32_t d, int32_t S,
+                            int32_t B, float lr, float reg, float reg_adv, float eps, int32_t adver, void* ws,
+                            int64_t ws_bytes, float* stats, int32_t step, int32_t stage, apr_stream_t stream) {
+  return stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws, ws_bytes,
+                            stats, step, stage, nullptr, stream);
 }
 
 // Cross-rank barrier on peer-mapped signal words: rank r stores `epoch` into slot [r] of every peer's signal array and
@@ -1751,7 +1969,9 @@ __global__ void xbarrier_launch(SigArray sig, int nranks, int rank, int epoch, i
   do {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
     if (v >= epoch) break;
-    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); break; }
+    // a peer that is ~2 s late (or an earlier time-out of this rank): set *err -- every later stage kernel of this call
+    // then returns at once (StepCtx::abort) instead of reading tables the peers are still writing, and the host raises
+    if (*reinterpret_cast<volatile int*>(err) || clock64() - t0 > 4000000000LL) { atomicExch(err, 1); break; }
     __nanosleep(64);
   } while (true);
   __threadfence_system();
@@ -1795,15 +2015,15 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
       APR_CUDA_CHECK(cudaEventRecord(ax.fork, st));
       APR_CUDA_CHECK(cudaStreamWaitEvent(ax.fast_stream, ax.fork, 0));
       if (timing) cudaEventRecord(ev[6], ax.fast_stream);
-      const int r2 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
-                                             adver, ws, ws_bytes, stats, s, 3, ax.fast_stream);
+      const int r2 = stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
+                                        adver, ws, ws_bytes, stats, s, 3, err, ax.fast_stream);
       if (r2) return r2;
       APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.fast_stream));
       if (timing) cudaEventRecord(ev[7], ax.fast_stream);
       if (pairs_enabled(d)) {   // pair work units: third stream, no ordering against the other kernels of the step
         APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
-        const int r3 = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
-                                               adver, ws, ws_bytes, stats, s, 4, ax.pair_stream);
+        const int r3 = stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps,
+                                          adver, ws, ws_bytes, stats, s, 4, err, ax.pair_stream);
         if (r3) return r3;
         APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
       }
@@ -1812,22 +2032,22 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
     if (order == 0 || !adver) { if ((rc = launch_fast())) return rc; }
     if (timing) cudaEventRecord(ev[0], st);
     if (adver) {
-      rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
-                                   ws_bytes, stats, s, 0, st);
+      rc = stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                              ws_bytes, stats, s, 0, err, st);
       if (rc) return rc;
       if (timing) cudaEventRecord(ev[1], st);
       if ((rc = barrier())) return rc;
       if (order == 1) { if ((rc = launch_fast())) return rc; }
     }
     if (timing) cudaEventRecord(ev[2], st);
-    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
-                                 ws_bytes, stats, s, 1, st);
+    rc = stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                            ws_bytes, stats, s, 1, err, st);
     if (rc) return rc;
     if (timing) cudaEventRecord(ev[3], st);
     if ((rc = barrier())) return rc;
     if (timing) cudaEventRecord(ev[4], st);
-    rc = apr_train_stage_sharded(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
-                                 ws_bytes, stats, s, 2, st);
+    rc = stage_sharded_impl(Pb, Qb, accPb, accQb, GQb, HQb, nranks, rank, d, S, B, lr, reg, reg_adv, eps, adver, ws,
+                            ws_bytes, stats, s, 2, err, st);
     if (rc) return rc;
     if (timing) cudaEventRecord(ev[5], st);
     if (order == 2 && adver) { if ((rc = launch_fast())) return rc; }
@@ -1853,6 +2073,16 @@ int apr_train_steps_sharded(float* const* Pb, float* const* Qb, float* const* ac
               1e3 * acc_ms[4] / count, 1e3 * acc_ms[5] / count, 1e3 * acc_ms[6] / count);
     for (auto& e : ev) cudaEventDestroy(e);
   }
+  return APR_OK;
+}
+
+/* Synchronises the stream and returns the workspace's sticky status word: bit 0 = an id outside its table reached the
+ * index preparation since apr_train_workspace_init (such a triple trained row 0 instead of faulting). */
+int apr_train_status(const void* ws, int32_t* flags_host, apr_stream_t stream) {
+  if (!ws || !flags_host) return APR_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  APR_CUDA_CHECK(cudaMemcpyAsync(flags_host, ws, 4, cudaMemcpyDeviceToHost, st));
+  APR_CUDA_CHECK(cudaStreamSynchronize(st));
   return APR_OK;
 }
 

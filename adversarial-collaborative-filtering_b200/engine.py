@@ -132,7 +132,7 @@ def _train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, w
         raise ValueError("accumulator shape mismatch")
     return (_ptr(P, torch.float32), _ptr(Q, torch.float32), _ptr(accP, torch.float32), _ptr(accQ, torch.float32),
             P.shape[0], Q.shape[0], d, _ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), S, B, float(lr),
-            float(reg), float(reg_adv), float(eps), int(bool(adver)), int(mode), ws.buf.data_ptr(), ws.nbytes,
+            float(reg), float(reg_adv), float(eps), int(adver), int(mode), ws.buf.data_ptr(), ws.nbytes,
             _ptr(stats, torch.float32), _stream())
 
 
@@ -142,6 +142,22 @@ def train_steps(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, ws: Tra
     _lib.check(_lib.lib().apr_train_steps(*_train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, adver, mode, ws, stats)))
     touch(P)
     touch(Q)
+
+
+def train_steps_random(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, ws: TrainWorkspace, noise_seed: int,
+                       noise_first_step: int, stats: Optional[torch.Tensor] = None) -> None:
+    """training_batch with ``--adv random`` (APR.py:170-177): step s uses the noise of global step noise_first_step + s."""
+    a = _train_args(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, 1, 0, ws, stats)
+    _lib.check(_lib.lib().apr_train_steps_random(*a[:16], noise_seed & 0xFFFFFFFF, noise_first_step & 0xFFFFFFFF, *a[18:]))
+    touch(P)
+    touch(Q)
+
+
+def train_status(ws: TrainWorkspace) -> int:
+    """Sticky status word of the workspace (synchronises): bit 0 = an out-of-range id reached the index preparation."""
+    f = ctypes.c_int32(0)
+    _lib.check(_lib.lib().apr_train_status(ws.buf.data_ptr(), ctypes.byref(f), _stream()))
+    return int(f.value)
 
 
 def train_prepare(P, Q, u, i, j, ws: TrainWorkspace) -> None:

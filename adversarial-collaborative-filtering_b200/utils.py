@@ -104,14 +104,17 @@ def as_device_batches(x, device) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------
 def training_batch(model, sess, batches, adver=False):
     """For every batch: [if adver: update_P/update_Q] then the optimizer (dns == 1); with dns > 1 the best-scored of
-    the dns sampled negatives is chosen per positive and there is no adversarial update (utils.py:121-139)."""
+    the dns sampled negatives is chosen per positive and there is no adversarial update (utils.py:121-139) -- but the
+    optimizer is still the one of the graph the model was built with: on an adversarial model (args.adver) it minimises
+    L + reg_adv L_adv + 2 reg-terms with Delta == 0, i.e. a plain step scaled by (1 + reg_adv) (engine adver mode 3).
+    Ids outside the tables raise at the end of the call (the reference's embedding_lookup raises InvalidArgument)."""
     user_input, item_input_pos, user_dns_list, item_dns_list = batches
     dev = model.device
     U = as_device_batches(user_input, dev)
     I = as_device_batches(item_input_pos, dev)
     if model.dns == 1:
         J = as_device_batches(item_dns_list, dev)
-        sess.train_steps(model, U, I, J, adver=bool(adver))
+        sess.train_steps(model, U, I, J, adver=bool(adver), check=True)
         item_input_neg = item_dns_list
     else:
         UD = as_device_batches(user_dns_list, dev)
@@ -121,15 +124,10 @@ def training_batch(model, sess, batches, adver=False):
         for s in range(S):
             # the choice must see the parameters as updated by the previous batches
             J[s] = engine.select_dns(model.embedding_P, model.embedding_Q, UD[s].contiguous(), JD[s].contiguous(), model.dns)
-            sess.train_steps(model, U[s:s + 1], I[s:s + 1], J[s:s + 1], adver=False)
+            sess.train_steps(model, U[s:s + 1], I[s:s + 1], J[s:s + 1], adver=3 if model.adver else 0)
+        sess.check(model)
         item_input_neg = DeviceBatches(J)
     return user_input, item_input_pos, item_input_neg
-
-
-def adv_update(model, sess, train_batches):
-    """utils.py:143-154 builds Delta from ALL batches at once; unused by the drivers.  Delta tables do not exist in
-    this implementation (they live in the per-step workspace), so this is not offered."""
-    raise NotImplementedError("adv_update is unused by the reference drivers; Delta is not a persistent table here")
 
 
 def training_loss_acc(model, sess, train_batches, output_adv):

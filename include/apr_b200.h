@@ -107,6 +107,24 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
                     const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, float lr,
                     float reg, float reg_adv, float eps, int32_t adver, int32_t mode, void* workspace,
                     int64_t workspace_bytes, float* stats, apr_stream_t stream);
+/* adver (all training entry points): 0 = BPR step; 1 = APR, Delta from the batch gradient (--adv grad); 3 = the
+ * reference's dns > 1 branch on an adversarial graph (utils.py:121-139: the optimizer of the adversarial loss with
+ * Delta == 0, i.e. data term x (1 + reg_adv), regulariser counted twice); 2 is rejected here -- `--adv random` is
+ * apr_train_steps_random:
+ *
+ * ---- A5' `--adv random`, APR.py:170-177 (shape-consistent form evaluation_adv.py:182-189): before every step
+ *      Delta_P = eps * l2_normalize(truncated_normal([rows, d], 0, 0.01)), Delta_Q likewise, fresh for ALL rows.  Only
+ *      touched rows matter, so each row's noise is generated where the row is used (Philox: element = row * d + col,
+ *      table id = 2 * global_step + {0: P, 1: Q}, key = (noise_seed, stream ADV); oracle.random_delta) -- never a
+ *      [rows, d] table.  Step s of the call uses global step noise_first_step + s. */
+int apr_train_steps_random(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, int64_t rows_q, int32_t d,
+                           const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, float lr,
+                           float reg, float reg_adv, float eps, uint32_t noise_seed, uint32_t noise_first_step,
+                           void* workspace, int64_t workspace_bytes, float* stats, apr_stream_t stream);
+/* Synchronises and returns the workspace's sticky status word: bit 0 = an id outside its table reached the index
+ * preparation since apr_train_workspace_init (that triple trained row 0 instead of faulting; the reference's
+ * embedding_lookup raises InvalidArgument).  apr_b200.APR.Session raises on it at the end of every training_batch. */
+int apr_train_status(const void* workspace, int32_t* flags_host, apr_stream_t stream);
 /* The two halves of apr_train_steps, exposed so the index preparation (hash de-duplication of the rows each batch
  * touches) can be timed and profiled separately from the embedding kernels. */
 int apr_train_prepare(const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch, int32_t d,

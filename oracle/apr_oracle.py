@@ -356,9 +356,37 @@ def adagrad_apply(W, A, g, lr):
     W[touched] -= dt.type(lr) * g[touched] / np.sqrt(A[touched])
 
 
+STREAM_ADV = 0x41445631
+
+
+def random_delta(n_rows: int, d: int, eps: float, seed: int, step: int, table: int) -> np.ndarray:
+    """``--adv random`` (APR.py:170-177; shape-consistent form evaluation_adv.py:182-189):
+    Delta = eps * l2_normalize(truncated_normal([rows, d], 0, 0.01), 1), drawn afresh at every step.  The draw of
+    global step ``step`` for table ``table`` (0: P, 1: Q) is the counter-based table (2*step + table) of stream ADV."""
+    z = truncated_normal(n_rows, d, 0.01, seed, ((step << 1) | table) & 0xFFFFFFFF, STREAM_ADV)
+    return l2_normalize_eps(z, eps)
+
+
+def apr_step_random(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, seed, step):
+    """One batch of ``training_batch`` with ``--adv random``: update_P/update_Q assign the noise Delta
+    (APR.py:176-177), then the optimizer runs on L + reg_adv L_adv + reg-terms (APR.py:158-165,195)."""
+    dP = random_delta(P.shape[0], P.shape[1], eps, seed, step, 0)
+    dQ = random_delta(Q.shape[0], Q.shape[1], eps, seed, step, 1)
+    gP, gQ, dP, dQ, info = step_gradients(P, Q, u, i, j, reg, reg_adv, eps, 1, dP, dQ)
+    adagrad_apply(P, accP, gP, lr)
+    adagrad_apply(Q, accQ, gQ, lr)
+    info.update({"gP": gP, "gQ": gQ, "dP": dP, "dQ": dQ})
+    return info
+
+
 def apr_step(P, Q, accP, accQ, u, i, j, lr, reg=0.0, reg_adv=1.0, eps=0.5, adver=1):
-    """One batch of ``training_batch`` (utils.py:113-119), in place.  Returns info dict."""
-    gP, gQ, dP, dQ, info = step_gradients(P, Q, u, i, j, reg, reg_adv, eps, adver)
+    """One batch of ``training_batch`` (utils.py:113-119), in place.  Returns info dict.
+    ``adver`` = 3: the dns > 1 branch on an adversarial graph (utils.py:121-139): update_P/update_Q never run there, so
+    the optimizer sees opt_loss = L + reg_adv L_adv + 2 reg-terms with Delta == 0."""
+    if adver == 3:
+        gP, gQ, dP, dQ, info = step_gradients(P, Q, u, i, j, reg, reg_adv, eps, 1, np.zeros_like(P), np.zeros_like(Q))
+    else:
+        gP, gQ, dP, dQ, info = step_gradients(P, Q, u, i, j, reg, reg_adv, eps, adver)
     adagrad_apply(P, accP, gP, lr)
     adagrad_apply(Q, accQ, gQ, lr)
     info.update({"gP": gP, "gQ": gQ, "dP": dP, "dQ": dQ})

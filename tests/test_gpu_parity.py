@@ -25,6 +25,17 @@ def _close(got, ref, rtol=RTOL):
     assert err <= rtol, "max error %.3g of scale %.3g" % (err * scale, scale)
 
 
+def _close_update(got, ref, before, rtol=RTOL):
+    """The north_star bar on what a step CHANGES: |(got - before) - (ref - before)| <= rtol * max|ref - before|.
+    (`_close` on the tables themselves is ~10x looser, because an update is ~1e-2 of a 0.1-scale table; the Adagrad
+    kernels use MUFU.RSQ and __fdividef, so this is the check that bounds them.)"""
+    got, ref, before = [np.asarray(a, dtype=np.float64) for a in (got, ref, before)]
+    dg, dr = got - before, ref - before
+    scale = max(float(np.abs(dr).max()), 1e-30)
+    err = float(np.abs(dg - dr).max()) / scale
+    assert err <= rtol, "update error %.3g of update scale %.3g" % (err * scale, scale)
+
+
 def _dev(a, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
 
@@ -104,6 +115,92 @@ def test_train_steps_match_oracle(cuda_device, mode, adver, d, U, I, S, B, zipf)
     for s in range(S):  # exact unique-row counts feed the roofline byte model
         assert counts[s, 0] == np.unique(u[s]).size
         assert counts[s, 1] == np.unique(np.concatenate([i[s], j[s]])).size
+    # one step, measured on the UPDATE: embeddings' and accumulators' changes within 1e-5 of the update's own scale
+    r1 = _run_oracle_steps(P, Q, u[:1], i[:1], j[:1], lr, reg, reg_adv, eps, adver)
+    g1 = _run_cuda_steps(cuda_device, P, Q, u[:1], i[:1], j[:1], lr, reg, reg_adv, eps, adver, mode)
+    _close_update(g1[0], r1[0], P)
+    _close_update(g1[1], r1[1], Q)
+    _close_update(g1[2], r1[2], np.full_like(P, 0.1))
+    _close_update(g1[3], r1[3], np.full_like(Q, 0.1))
+
+
+@pytest.mark.parametrize("d,U,I,S,B,zipf", [(64, 300, 200, 4, 512, False), (128, 5000, 3000, 2, 2048, False),
+                                            (24, 64, 64, 3, 100, True), (256, 700, 900, 2, 300, True),
+                                            (64, 100000, 50000, 2, 1024, False)])
+def test_adv_random_matches_oracle(cuda_device, d, U, I, S, B, zipf):
+    """`--adv random` (A5', APR.py:170-177): Delta = eps * l2_normalize(truncated_normal) drawn afresh per step for every
+    row, generated where a row is touched (Philox keyed by (seed, global step, table, row, column)) -- against the oracle
+    that materialises the two noise tables.  Duplicated users / items, pair work units and fast segments all occur."""
+    from apr_b200 import engine
+    rng = np.random.RandomState(d + B + 1)
+    P, Q, u, i, j = _problem(rng, U, I, d, S, B, zipf=zipf)
+    lr, reg, reg_adv, eps, seed, step0 = 0.05, 0.01, 1.0, 0.5, 2019, 7
+    rP, rQ = P.copy(), Q.copy()
+    raP, raQ = np.full_like(P, 0.1), np.full_like(Q, 0.1)
+    rstats = []
+    for s in range(S):
+        rstats.append(O.loss_acc(rP, rQ, u[s], i[s], j[s]))
+        O.apr_step_random(rP, rQ, raP, raQ, u[s], i[s], j[s], lr, reg, reg_adv, eps, seed, step0 + s)
+        if s == 0:
+            first = [a.copy() for a in (rP, rQ, raP, raQ)]
+    dev = cuda_device
+    for n_steps in (S, 1):
+        tP, tQ = _dev(P, torch.float32, dev), _dev(Q, torch.float32, dev)
+        aP, aQ = torch.full_like(tP, 0.1), torch.full_like(tQ, 0.1)
+        ws = engine.TrainWorkspace(n_steps, B, d, dev)
+        stats = torch.zeros((n_steps, 2), dtype=torch.float32, device=dev)
+        engine.train_steps_random(tP, tQ, aP, aQ, _dev(u[:n_steps], torch.int32, dev), _dev(i[:n_steps], torch.int32, dev),
+                                  _dev(j[:n_steps], torch.int32, dev), lr, reg, reg_adv, eps, ws, seed, step0, stats=stats)
+        got = [t.cpu().numpy() for t in (tP, tQ, aP, aQ)]
+        if n_steps == S:
+            for g, r in zip(got, (rP, rQ, raP, raQ)):
+                _close(g, r)
+            st = stats.cpu().numpy()
+            _close(st[:, 0], np.asarray(rstats)[:, 0])
+            assert np.array_equal(st[:, 1].astype(np.int64), np.asarray(rstats)[:, 1].astype(np.int64))
+        else:
+            for g, r, b in zip(got, first, (P, Q, np.full_like(P, 0.1), np.full_like(Q, 0.1))):
+                _close_update(g, r, b)
+
+
+def test_dns_branch_on_adversarial_graph(cuda_device):
+    """utils.py:121-139 with args.adver = 1 and dns > 1: no update_P/update_Q, but the optimizer is the adversarial
+    graph's (opt_loss with Delta == 0): data term x (1 + reg_adv), regulariser counted twice (engine adver mode 3)."""
+    rng = np.random.RandomState(33)
+    P, Q, u, i, j = _problem(rng, 300, 200, 64, 3, 512)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 0.7, 0.5
+    for mode in (0, 1, 2):
+        r = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, 3)
+        g = _run_cuda_steps(cuda_device, P, Q, u, i, j, lr, reg, reg_adv, eps, 3, mode)
+        for a, b in zip(g[:4], r[:4]):
+            _close(a, b)
+    r1 = _run_oracle_steps(P, Q, u[:1], i[:1], j[:1], lr, reg, reg_adv, eps, 3)
+    g1 = _run_cuda_steps(cuda_device, P, Q, u[:1], i[:1], j[:1], lr, reg, reg_adv, eps, 3, 0)
+    _close_update(g1[0], r1[0], P)
+    _close_update(g1[1], r1[1], Q)
+    # and it differs from the plain BPR step (what round 1 ran in this branch)
+    b1 = _run_oracle_steps(P, Q, u[:1], i[:1], j[:1], lr, reg, reg_adv, eps, 0)
+    assert np.abs(b1[0] - r1[0]).max() > 1e-4
+
+
+def test_out_of_range_ids_raise(cuda_device):
+    """An id outside its table must not train silently (the reference's embedding_lookup raises InvalidArgument): the
+    Session surfaces the index preparation's flag at the end of training_batch."""
+    import types
+
+    from apr_b200.APR import MF, Session
+    args = types.SimpleNamespace(embed_size=16, lr=0.05, reg=0.0, dns=1, adv="grad", eps=0.5, adver=1, reg_adv=1.0, epochs=1)
+    model = MF(50, 40, args)
+    model.build_graph()
+    rng = np.random.RandomState(1)
+    u = rng.randint(0, 50, (2, 64)).astype(np.int32)
+    i = rng.randint(0, 40, (2, 64)).astype(np.int32)
+    j = rng.randint(0, 40, (2, 64)).astype(np.int32)
+    sess = Session()
+    sess.train_steps(model, *[_dev(x, torch.int32, cuda_device) for x in (u, i, j)], adver=True, check=True)   # fine
+    i[1, 5] = 41 + model.extra_row      # one past the last row
+    with pytest.raises(IndexError):
+        sess.train_steps(model, *[_dev(x, torch.int32, cuda_device) for x in (u, i, j)], adver=True, check=True)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])

@@ -101,6 +101,44 @@ def test_step_matches_torch_autograd_and_adagrad(adver, reg):
     assert np.allclose(Q, tQ.detach().numpy(), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("variant", ["random", "delta_zero"])
+def test_given_delta_steps_match_torch_autograd(variant):
+    """`--adv random` (APR.py:170-177: Delta = eps * l2_normalize(noise), a constant of the step) and the dns > 1 branch
+    on an adversarial graph (utils.py:121-139: Delta == 0) against torch autograd + Adagrad of opt_loss as written in
+    APR.py:153-165, fp64."""
+    rng = np.random.RandomState(5)
+    U, I, d, B = 13, 9, 8, 40
+    P = rng.randn(U, d) * 0.5
+    Q = rng.randn(I, d) * 0.5
+    u, i, j = rng.randint(0, U, B), rng.randint(0, I, B), rng.randint(0, I, B)
+    lr, reg, reg_adv, eps, seed, step = 0.05, 0.01, 0.7, 0.5, 2019, 11
+    accP, accQ = np.full_like(P, 0.1), np.full_like(Q, 0.1)
+    P0, Q0 = P.copy(), Q.copy()
+    if variant == "random":
+        info = O.apr_step_random(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, seed, step)
+        dP, dQ = info["dP"], info["dQ"]
+        assert np.allclose(np.linalg.norm(dP, axis=1), eps, rtol=1e-5)       # every row: length eps
+        assert np.array_equal(dP, O.random_delta(U, d, eps, seed, step, 0))  # counter-based: reproducible
+        assert not np.array_equal(dP, O.random_delta(U, d, eps, seed, step + 1, 0))   # fresh noise at every step
+        assert not np.array_equal(dP[:I], dQ)                                # P and Q tables differ
+    else:
+        info = O.apr_step(P, Q, accP, accQ, u, i, j, lr, reg, reg_adv, eps, 3)
+        dP, dQ = np.zeros_like(P0), np.zeros_like(Q0)
+    tP = torch.tensor(P0, requires_grad=True)
+    tQ = torch.tensor(Q0, requires_grad=True)
+    tu, ti, tj = [torch.tensor(x, dtype=torch.long) for x in (u, i, j)]
+    opt = torch.optim.Adagrad([tP, tQ], lr=lr, initial_accumulator_value=0.1, eps=0.0)
+    _, opt_loss = _torch_loss(tP, tQ, torch.tensor(dP.astype(np.float64)), torch.tensor(dQ.astype(np.float64)), tu, ti, tj,
+                              reg, reg_adv, 1)
+    opt.zero_grad()
+    opt_loss.backward()
+    assert np.allclose(info["gP"], tP.grad.numpy(), rtol=1e-9, atol=1e-12)
+    assert np.allclose(info["gQ"], tQ.grad.numpy(), rtol=1e-9, atol=1e-12)
+    opt.step()
+    assert np.allclose(P, tP.detach().numpy(), rtol=1e-9, atol=1e-12)
+    assert np.allclose(Q, tQ.detach().numpy(), rtol=1e-9, atol=1e-12)
+
+
 def test_clip_blocks_gradient_outside_interval():
     P = np.array([[40.0, 0.0]], dtype=np.float64)
     Q = np.array([[0.0, 0.0], [3.0, 0.0]], dtype=np.float64)
