@@ -242,12 +242,14 @@ def _cached_device(key, arr: np.ndarray, dtype, device) -> torch.Tensor:
     return t[0]
 
 
-def shuffle(samples, batch_size, dataset, model, epoch: Optional[int] = None, rank: int = 0, world: int = 1):
+def shuffle(samples, batch_size, dataset, model, epoch: Optional[int] = None, rank: int = 0, world: int = 1,
+            fork_workers: Optional[int] = None):
     """APR.py:39-61 on the GPU: epoch permutation + ``model.dns`` uniform negatives per positive, rejected against
     trainList[u]; tail batch dropped.  Counter-based: the result depends only on (model.seed, epoch).  ``epoch``
     defaults to the number of previous shuffle calls on this model.  Returns four DeviceBatches.
     Data-parallel runs: rank r of ``world`` gets columns [r*B/world, (r+1)*B/world) of every batch of the SAME epoch
-    (bit-identical slices, no collective: SURVEY 8e)."""
+    (bit-identical slices, no collective: SURVEY 8e).  ``fork_workers`` (default: model.fork_workers, 0) > 0 emulates
+    the reference's fork-duplicated negative streams -- for comparing against its logs only."""
     if epoch is None:
         epoch = model.shuffle_count
     model.shuffle_count += 1
@@ -261,7 +263,8 @@ def shuffle(samples, batch_size, dataset, model, epoch: Optional[int] = None, ra
     ptr = _cached_device("csr_ptr", ptr_h, torch.int64, dev)
     idx = _cached_device("csr_idx", idx_h, torch.int32, dev)
     u, i, ud, j, err = engine.sample_epoch(pu, pi, batch_size, dataset.num_items, ptr, idx, model.seed, epoch, model.dns,
-                                           rank=rank, world=world)
+                                           rank=rank, world=world,
+                                           fork_workers=getattr(model, "fork_workers", 0) if fork_workers is None else fork_workers)
     model._sampler_err = err
     return DeviceBatches(u), DeviceBatches(i), DeviceBatches(ud), DeviceBatches(j)
 

@@ -89,7 +89,7 @@ _SIGNATURES = {
     "apr_sample_epoch": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_uint32, c_uint32, c_int32,
                                         _P, _P, _P, _P, _P, _P]),
     "apr_sample_epoch_shard": (ctypes.c_int, [_P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_uint32, c_uint32, c_int32,
-                                              c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
+                                              c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P]),
     "apr_select_dns": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, c_int32, _P, _P]),
     "apr_train_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "apr_train_workspace_init": (ctypes.c_int, [_P, c_int64, _P]),

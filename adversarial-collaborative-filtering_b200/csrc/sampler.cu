@@ -2,6 +2,8 @@
 //
 // Replaces shuffle/_get_train_batch (APR.py:39-81), the dns>1 branch of training_batch (utils.py:121-139) and
 // MF._create_variables (APR.py:105-119).  Integer outputs are bit-identical to oracle/apr_oracle.py.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace apr {
@@ -12,7 +14,8 @@ __global__ void __launch_bounds__(256)
 sample_epoch_kernel(const int32_t* __restrict__ pairs_u, const int32_t* __restrict__ pairs_i, uint32_t n_pairs,
                     int64_t n_draws, int dns, uint32_t num_items, const int64_t* __restrict__ csr_ptr,
                     const int32_t* __restrict__ csr_idx, int csr_rows, uint32_t seed, uint32_t epoch, PermKeys keys,
-                    int half_bits, int batch, int batch_lo, int batch_local, int32_t* __restrict__ out_u,
+                    int half_bits, int batch, int batch_lo, int batch_local, int64_t fork_chunk_draws, int fork_workers,
+                    int32_t* __restrict__ out_u,
                     int32_t* __restrict__ out_i, int32_t* __restrict__ out_udns, int32_t* __restrict__ out_j,
                     int32_t* err_flag) {
   // a rank of a sharded run draws the triples [batch_lo, batch_lo + batch_local) of every batch: `fl` numbers ITS draws,
@@ -23,13 +26,15 @@ sample_epoch_kernel(const int32_t* __restrict__ pairs_u, const int32_t* __restri
     const int k = int(fl - tl * dns);
     const int64_t step = tl / batch_local;
     const int64_t t = step * batch + batch_lo + (tl - step * batch_local);
-    const int64_t f = t * dns + k;
+    int64_t f = t * dns + k;
     const uint32_t pair = feistel_perm(uint32_t(t), n_pairs, half_bits, keys);
     const int32_t user = pairs_u[pair];
     if (k == 0) { out_u[tl] = user; out_i[tl] = pairs_i[pair]; }
     out_udns[fl] = user;
     int64_t lo = 0, hi = 0;
     if (user < csr_rows) { lo = csr_ptr[user]; hi = csr_ptr[user + 1]; }
+    // legacy mode (oracle.fork_counter): the W chunks of one pool.map round share one random stream
+    if (fork_workers > 0) f = ((f / fork_chunk_draws) / fork_workers) * fork_chunk_draws + (f % fork_chunk_draws);
     uint32_t w[4];
     int32_t chosen = -1;
     for (int attempt = 0; attempt < kMaxNegAttempts; ++attempt) {
@@ -96,11 +101,11 @@ extern "C" {
 int apr_sample_epoch_shard(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch,
                            int32_t num_items, const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows,
                            uint32_t seed, uint32_t epoch, int32_t dns, int32_t batch_lo, int32_t batch_local,
-                           int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
-                           apr_stream_t stream) {
+                           int32_t legacy_fork_workers, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j,
+                           int32_t* err_flag, apr_stream_t stream) {
   if (!pairs_u || !pairs_i || !csr_ptr || !out_u || !out_i || !out_udns || !out_j || !err_flag) return APR_E_ARG;
   if (n_pairs < 1 || n_pairs > 0x7fffffffLL || batch < 1 || num_items < 1 || dns < 1 || csr_rows < 0) return APR_E_ARG;
-  if (batch_lo < 0 || batch_local < 1 || batch_lo + batch_local > batch) return APR_E_ARG;
+  if (batch_lo < 0 || batch_local < 1 || batch_lo + batch_local > batch || legacy_fork_workers < 0) return APR_E_ARG;
   const int64_t S = n_pairs / batch;
   if (S < 1) return APR_E_ARG;
   const int64_t n_draws = S * batch_local * dns;
@@ -113,11 +118,14 @@ int apr_sample_epoch_shard(const int32_t* pairs_u, const int32_t* pairs_i, int64
   while ((int64_t(1) << bits) < n_pairs) ++bits;  // bit_length(n-1)
   if (bits < 2) bits = 2;
   bits += bits & 1;
+  int64_t fork_chunk_draws = 1;
+  if (legacy_fork_workers > 0)
+    fork_chunk_draws = std::max<int64_t>(1, (S + 4 * int64_t(legacy_fork_workers) - 1) / (4 * int64_t(legacy_fork_workers))) * batch * dns;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   sample_epoch_kernel<<<grid_for(n_draws, 256), 256, 0, st>>>(pairs_u, pairs_i, uint32_t(n_pairs), n_draws, dns,
                                                               uint32_t(num_items), csr_ptr, csr_idx, csr_rows, seed, epoch,
-                                                              keys, bits / 2, batch, batch_lo, batch_local, out_u, out_i,
-                                                              out_udns, out_j, err_flag);
+                                                              keys, bits / 2, batch, batch_lo, batch_local, fork_chunk_draws,
+                                                              legacy_fork_workers, out_u, out_i, out_udns, out_j, err_flag);
   APR_LAUNCH_CHECK();
   return APR_OK;
 }
@@ -127,7 +135,7 @@ int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_p
                      int32_t dns, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
                      apr_stream_t stream) {
   return apr_sample_epoch_shard(pairs_u, pairs_i, n_pairs, batch, num_items, csr_ptr, csr_idx, csr_rows, seed, epoch, dns, 0,
-                                batch, out_u, out_i, out_udns, out_j, err_flag, stream);
+                                batch, 0, out_u, out_i, out_udns, out_j, err_flag, stream);
 }
 
 int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_dns, const int32_t* j_dns, int64_t n_pos,

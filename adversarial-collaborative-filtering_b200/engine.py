@@ -66,7 +66,8 @@ def fill(x: torch.Tensor, value: float) -> None:
 
 
 def sample_epoch(pairs_u: torch.Tensor, pairs_i: torch.Tensor, batch: int, num_items: int, csr_ptr: torch.Tensor,
-                 csr_idx: torch.Tensor, seed: int, epoch: int, dns: int = 1, rank: int = 0, world: int = 1):
+                 csr_idx: torch.Tensor, seed: int, epoch: int, dns: int = 1, rank: int = 0, world: int = 1,
+                 fork_workers: int = 0):
     """-> (u[S,Bl], i[S,Bl], u_dns[S,Bl*dns], j[S,Bl*dns], err) int32 device tensors (APR.py:39-81).
     ``batch`` is the GLOBAL batch; with world > 1 this rank draws its slice [rank*Bl, (rank+1)*Bl) of every batch,
     Bl = batch // world -- bit-identical to the same columns of the world == 1 result (no collective)."""
@@ -86,7 +87,7 @@ def sample_epoch(pairs_u: torch.Tensor, pairs_i: torch.Tensor, batch: int, num_i
     _lib.check(_lib.lib().apr_sample_epoch_shard(_ptr(pairs_u, torch.int32), _ptr(pairs_i, torch.int32), n, batch, num_items,
                                                  _ptr(csr_ptr, torch.int64), _ptr(csr_idx, torch.int32) if csr_idx.numel() else 0,
                                                  csr_ptr.numel() - 1, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, dns, rank * bl, bl,
-                                                 _ptr(u), _ptr(i), _ptr(ud), _ptr(j), _ptr(err), _stream()))
+                                                 int(fork_workers), _ptr(u), _ptr(i), _ptr(ud), _ptr(j), _ptr(err), _stream()))
     return u, i, ud, j, err
 
 

@@ -76,12 +76,15 @@ int apr_sample_epoch(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_p
  * triples [batch_lo, batch_lo + batch_local) of every batch -- outputs out_u/out_i [S*batch_local], out_udns/out_j
  * [S*batch_local*dns].  Every random number is keyed by the triple's index in the WHOLE epoch, so the shards are
  * bit-identical slices of apr_sample_epoch's output and no collective is needed (rank r of G passes
- * batch_lo = r * batch / G, batch_local = batch / G). */
+ * batch_lo = r * batch / G, batch_local = batch / G).
+ * legacy_fork_workers > 0 reproduces, statistically, the reference's fork-duplicated negative streams (SURVEY B.3:
+ * Pool(cpu_count()) forked after the shuffle, every worker starting from the parent's RNG state): the W chunks of one
+ * pool.map round share one counter range (oracle.fork_counter).  0 = independent draws (the default everywhere). */
 int apr_sample_epoch_shard(const int32_t* pairs_u, const int32_t* pairs_i, int64_t n_pairs, int32_t batch,
                            int32_t num_items, const int64_t* csr_ptr, const int32_t* csr_idx, int32_t csr_rows,
                            uint32_t seed, uint32_t epoch, int32_t dns, int32_t batch_lo, int32_t batch_local,
-                           int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j, int32_t* err_flag,
-                           apr_stream_t stream);
+                           int32_t legacy_fork_workers, int32_t* out_u, int32_t* out_i, int32_t* out_udns, int32_t* out_j,
+                           int32_t* err_flag, apr_stream_t stream);
 
 /* ---- A7 (dns > 1 branch), utils.py:121-139: for each positive keep the best-scored of its dns negatives
  *      (first maximum wins).  u_dns/j_dns are [n_pos*dns]; out_j is [n_pos]. */

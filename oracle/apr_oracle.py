@@ -177,14 +177,25 @@ def _in_csr(ptr, idx, users, items) -> np.ndarray:
 MAX_NEG_ATTEMPTS = 1 << 16
 
 
+def fork_counter(f: np.ndarray, num_batch: int, batch_size: int, dns: int, workers: int) -> np.ndarray:
+    """Counter remap that emulates the reference's forked sampler (APR.py:51-56): Pool(workers) forked
+    AFTER np.random.shuffle, so every worker starts from the parent's RNG state and pool.map hands out chunks of
+    ceil(num_batch / (4*workers)) batches -- the W chunks of one round draw from the SAME random stream.  A draw with
+    epoch index f in chunk c = f // chunk_draws therefore takes the counter of round c // W at its offset in the chunk."""
+    chunk_draws = np.uint64(max(1, -(-num_batch // (4 * workers))) * batch_size * dns)
+    return ((f // chunk_draws) // np.uint64(workers)) * chunk_draws + (f % chunk_draws)
+
+
 def sample_epoch(pairs_u: np.ndarray, pairs_i: np.ndarray, batch_size: int, num_items: int,
-                 csr_ptr: np.ndarray, csr_idx: np.ndarray, seed: int, epoch: int, dns: int = 1):
+                 csr_ptr: np.ndarray, csr_idx: np.ndarray, seed: int, epoch: int, dns: int = 1, fork_workers: int = 0):
     """Counter-based restatement of ``shuffle`` + ``_get_train_batch`` (APR.py:39-81).
 
     Returns (u[S,B], i[S,B], u_dns[S,B*dns], j[S,B*dns]) int32.  Tail batch dropped (APR.py:52).
     Negative f = t*dns + k draws j = mulhi32(word, num_items) from Philox counter
     (f_lo, f_hi, attempt>>2, epoch), key (seed, STREAM_NEG), word index attempt&3, until
     j not in trainList[u]  (APR.py:76-78: range [0,num_items), held-out item MAY be drawn).
+    ``fork_workers`` > 0: the negatives' counters are remapped by ``fork_counter`` (the reference's fork-duplicated
+    streams, statistically); 0 = independent draws.
     """
     n = pairs_u.shape[0]
     S = n // batch_size
@@ -194,6 +205,8 @@ def sample_epoch(pairs_u: np.ndarray, pairs_i: np.ndarray, batch_size: int, num_
     u = pairs_u[pair].astype(np.int32)
     i = pairs_i[pair].astype(np.int32)
     f = (np.arange(T, dtype=np.uint64)[:, None] * np.uint64(dns) + np.arange(dns, dtype=np.uint64)[None, :]).ravel()
+    if fork_workers > 0:
+        f = fork_counter(f, S, batch_size, dns, fork_workers)
     uu = np.repeat(u, dns)
     j = np.full(f.shape, -1, dtype=np.int64)
     gkey = csr_gkey(csr_ptr, csr_idx)

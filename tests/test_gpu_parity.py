@@ -308,6 +308,12 @@ def test_sampler_bit_exact(cuda_device):
         assert int(got[4].item()) == 0
         for g, w in zip(got[:4], want):
             assert np.array_equal(g.cpu().numpy(), w)
+    # fork-emulating mode: the W chunks of a pool.map round share one counter range
+    want = O.sample_epoch(pu, pi, 64, I, ptr, idx, 2019, 1, 2, fork_workers=5)
+    got = engine.sample_epoch(_dev(pu, torch.int32, cuda_device), _dev(pi, torch.int32, cuda_device), 64, I,
+                              _dev(ptr, torch.int64, cuda_device), _dev(idx, torch.int32, cuda_device), 2019, 1, 2, fork_workers=5)
+    for g, w in zip(got[:4], want):
+        assert np.array_equal(g.cpu().numpy(), w)
 
 
 def test_sampler_rank_shards_are_slices_of_the_epoch(cuda_device):
