@@ -265,3 +265,128 @@ def train_steps_sharded(tables: ShardedTables, U: torch.Tensor, I: torch.Tensor,
             if aux_stream is not None:
                 main.wait_stream(aux_stream)
             stream_barrier(group, token)
+
+
+class ShardedTrainer(object):
+    """``training_batch`` on row-sharded tables with the index preparation and its exchange taken off the critical path.
+
+    Round 1 ran, per sub-chunk of steps, [index preparation on ONE rank] -> [9 broadcasts of its arrays] -> [the steps],
+    all on one stream: every rank idled while one prepared G times its own batch and nine NCCL launches shipped the
+    result (the serial fraction grew with G).  Here
+
+      * the rank's local triples are all_gathered, the sub-chunk is prepared (rank ``c % G`` for sub-chunk c, so the G
+        ranks prepare different sub-chunks concurrently), its nine regions are PACKED into one staging block, ONE
+        broadcast ships it and the receivers unpack -- all on a low-priority side stream;
+      * the step kernels of sub-chunk c wait only for that sub-chunk's "ready" event, so preparation and exchange of
+        sub-chunk c+1 (and of the next call: two workspaces alternate) run under the steps of c;
+      * the library issues every launch and cross-rank barrier of the steps (``apr_train_steps_sharded``); the barrier
+        error flag is checked by ``check()`` / at the end of ``train_steps(check=True)`` and raises.
+    """
+
+    REGIONS = ("ucnt", "icnt", "iall", "nslow", "seg_hdr", "rec", "iu_item", "npair", "pairs")
+
+    def __init__(self, tables: ShardedTables, steps_per_call: int, batch_local: int, group=None):
+        from . import engine
+        self.t, self.group = tables, group
+        self.G, self.rank, self.d, self.dev = tables.world, tables.rank, tables.d, tables.device
+        self.multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.S, self.Bl, self.Bg = steps_per_call, batch_local, batch_local * tables.world
+        self.ws = [engine.TrainWorkspace(self.S, self.Bg, self.d, self.dev) for _ in range(2)]
+        L = engine.train_layout(self.S, self.Bg, self.d)
+        self.Sc = L["Sc"]
+        Bg = self.Bg
+        step_bytes = {"ucnt": 4, "icnt": 4, "iall": 4, "nslow": 4, "seg_hdr": 32 * Bg, "rec": 16 * Bg, "iu_item": 4 * Bg,
+                      "npair": 4, "pairs": 48 * (Bg // 2 + 1)}
+        self.regions = [(L[n], step_bytes[n]) for n in self.REGIONS]
+        self.bytes_per_step = sum(-(-b // 16) * 16 for _, b in self.regions)
+        self.stage = torch.empty(self.bytes_per_step * self.Sc + 256, dtype=torch.uint8, device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.free = [None, None]          # recorded on the main stream after the steps of the call that used workspace k
+        self.keep = [None, None]          # the call's global batches (read by the side stream)
+        self.calls = 0
+
+    def _pack(self, ws, s0, ns, unpack: bool):
+        o = 0
+        for off, sb in self.regions:
+            n = sb * ns
+            a = ws.buf[off + s0 * sb: off + s0 * sb + n]
+            b = self.stage[o: o + n]
+            if unpack:
+                a.copy_(b, non_blocking=True)
+            else:
+                b.copy_(a, non_blocking=True)
+            o += -(-n // 16) * 16
+        return o
+
+    def train_steps(self, u_loc: torch.Tensor, i_loc: torch.Tensor, j_loc: torch.Tensor, lr, reg, reg_adv, eps, adver,
+                    stats: Optional[torch.Tensor] = None, check: bool = False, inputs_ready: Optional[torch.cuda.Event] = None):
+        """n <= steps_per_call steps; ``*_loc`` = THIS rank's triples [n, batch_local], int32, on the device or in
+        (pinned) host memory.  Device inputs must be complete when the call is made, or ``inputs_ready`` names the event
+        that says so (the side stream waits for it -- not the main stream, which is busy with the previous call's steps)."""
+        from . import engine
+        n = u_loc.shape[0]
+        assert n <= self.S and u_loc.shape[1] == self.Bl
+        k = self.calls & 1
+        self.calls += 1
+        ws = self.ws[k]
+        main = torch.cuda.current_stream(self.dev)
+        side = self.side
+        if self.free[k] is not None:
+            side.wait_event(self.free[k])                 # the steps that read this workspace two calls ago are done
+        if inputs_ready is not None:
+            side.wait_event(inputs_ready)
+        ready = []
+        with torch.cuda.stream(side):
+            glob = []
+            for x in (u_loc, i_loc, j_loc):
+                xl = x if x.is_cuda else x.to(self.dev, non_blocking=True)
+                if self.multi:
+                    g = torch.empty((self.G * n, self.Bl), dtype=torch.int32, device=self.dev)
+                    dist.all_gather_into_tensor(g, xl.contiguous(), group=self.group)
+                    glob.append(g.view(self.G, n, self.Bl).permute(1, 0, 2).reshape(n, self.Bg).contiguous())
+                else:
+                    glob.append(xl.contiguous())
+            self.keep[k] = glob
+            U, I, J = glob
+            for c, s0 in enumerate(range(0, n, self.Sc)):
+                ns = min(self.Sc, n - s0)
+                src = c % self.G
+                if not self.multi or src == self.rank:
+                    # the workspace is addressed by absolute step, the batches by step within this call: same thing here
+                    self._prepare(U, I, J, ws, n, s0, ns)
+                if self.multi:
+                    nbytes = self.bytes_per_step * ns
+                    if src == self.rank:
+                        self._pack(ws, s0, ns, unpack=False)
+                    gsrc = dist.get_global_rank(self.group, src) if self.group is not None else src
+                    dist.broadcast(self.stage[:nbytes], src=gsrc, group=self.group)
+                    if src != self.rank:
+                        self._pack(ws, s0, ns, unpack=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                ready.append((s0, ns, ev))
+        for s0, ns, ev in ready:
+            main.wait_event(ev)
+            engine.train_steps_sharded(self.t.ptrs, self.G, self.rank, self.d, self.S, self.Bg, lr, reg, reg_adv, eps, adver, ws,
+                                       s0, ns, self.t.err, None if stats is None else stats)
+        e = torch.cuda.Event()
+        e.record(main)
+        self.free[k] = e
+        if check:
+            self.check()
+
+    def _prepare(self, U, I, J, ws, n, s0, ns):
+        from . import engine
+        # the workspace layout is the one of steps_per_call steps whatever this call's length is
+        engine.train_prepare_range(self.t.rows_p, self.t.rows_q, U, I, J, ws, s0, ns, clear=True, n_steps=self.S)
+
+    def check(self) -> None:
+        """Raise if a cross-rank barrier timed out (a rank was ~2 s late: lazy module load, a hung peer).  The device side
+        has already stopped touching the tables (StepCtx::abort); synchronises."""
+        if int(self.t.err.item()) != 0:
+            raise RuntimeError("row-sharded training: a cross-rank barrier timed out on rank %d; the step was aborted"
+                               % self.rank)
+
+    def synchronize(self) -> None:
+        self.side.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

@@ -182,8 +182,15 @@ def train_layout(n_steps: int, batch: int, d: int) -> dict:
     return dict(zip(keys, [int(v) for v in out]))
 
 
-def train_prepare_range(rows_p: int, rows_q: int, u, i, j, ws: "TrainWorkspace", s0: int, ns: int, clear: bool = True) -> None:
+def train_prepare_range(rows_p: int, rows_q: int, u, i, j, ws: "TrainWorkspace", s0: int, ns: int, clear: bool = True,
+                        n_steps: Optional[int] = None) -> None:
+    """Index preparation of steps [s0, s0+ns).  ``n_steps`` = the step count the workspace LAYOUT is addressed with
+    (default: u.shape[0]); the batches only have to cover the prepared steps."""
     S, B = u.shape
+    if n_steps is not None:
+        if s0 + ns > S:
+            raise ValueError("batches do not cover steps [%d, %d)" % (s0, s0 + ns))
+        S = n_steps
     _lib.check(_lib.lib().apr_train_prepare_range(_ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), S, B,
                                                   ws.d, rows_p, rows_q, ws.buf.data_ptr(), ws.nbytes, s0, ns, int(clear),
                                                   _stream()))

@@ -44,7 +44,19 @@ def _train_worker(rank, world, port, out):
     ws = engine.TrainWorkspace(S, B, d, dev)
     aux = torch.cuda.Stream()
     td = lambda a: torch.from_numpy(a).to(dev)
-    train_steps_sharded(t, td(u), td(i), td(j), 0.05, 0.01, 1.0, 0.5, 1, ws, aux_stream=aux)
+    if os.environ.get("APR_TEST_TRAINER") == "1":
+        # the pipelined driver: every rank feeds ITS slice of each batch, three calls (both workspaces + a reuse), the
+        # last one shorter than steps_per_call
+        from apr_b200.distributed import ShardedTrainer
+        bl = B // world
+        tr = ShardedTrainer(t, 1, bl)
+        for s in range(S):
+            loc = [td(np.ascontiguousarray(x[s:s + 1, rank * bl:(rank + 1) * bl])) for x in (u, i, j)]
+            tr.train_steps(*loc, 0.05, 0.01, 1.0, 0.5, 1)
+        tr.synchronize()
+        tr.check()
+    else:
+        train_steps_sharded(t, td(u), td(i), td(j), 0.05, 0.01, 1.0, 0.5, 1, ws, aux_stream=aux)
     torch.cuda.synchronize()
     assert int(t.err.item()) == 0, "cross-rank barrier timed out"
     dist.barrier()
@@ -78,6 +90,23 @@ def test_row_sharded_training_two_gpus(tmp_path):
         assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.timeout(600)
+def test_row_sharded_training_pipelined_trainer_two_gpus(tmp_path, monkeypatch):
+    """ShardedTrainer (all_gather of the ranks' local triples, preparation + ONE packed broadcast per sub-chunk on a side
+    stream, alternating workspaces) gives the oracle's result for the same global batches."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("APR_TEST_TRAINER", "1")
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    full, P, Q, u, i, j = torch.load(out, weights_only=False)
+    aP, aQ = np.full_like(P, 0.1), np.full_like(Q, 0.1)
+    for s in range(u.shape[0]):
+        O.apr_step(P, Q, aP, aQ, u[s], i[s], j[s], 0.05, 0.01, 1.0, 0.5, 1)
+    for got, ref in ((full["P"], P), (full["Q"], Q), (full["accP"], aP), (full["accQ"], aQ)):
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def _eval_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -94,8 +123,13 @@ def _eval_worker(rank, world, port, out):
     test = rng.randint(0, I, U).astype(np.int32)
     ptr, idx = build_sorted_csr([train[k] + [int(test[k])] for k in range(U)])
     td = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
-    pos, ids, sc = evaluate_item_sharded_cuda(td(P, torch.float32), td(Q, torch.float32), td(np.arange(U), torch.int32),
-                                              td(test, torch.int32), I, td(ptr, torch.int64), td(idx, torch.int32), k_top=10)
+    from apr_b200.distributed import shard_bounds
+    lo, hi = shard_bounds(I, world, rank, 128)
+    # every rank holds ONLY its rows of the item table; held-out scores come from the owner (one all_reduce), counts are
+    # all_reduced, the per-shard top-10 lists merged by the apr_topk_merge kernel
+    pos, ids, sc = evaluate_item_sharded_cuda(td(P, torch.float32), td(Q[lo:hi], torch.float32), td(np.arange(U), torch.int32),
+                                              td(test, torch.int32), I, td(ptr, torch.int64), td(idx, torch.int32), k_top=10,
+                                              q_row_offset=lo)
     if rank == 0:
         torch.save((pos.cpu(), ids.cpu(), P, Q, train, test, I), out)
     dist.destroy_process_group()

@@ -489,6 +489,36 @@ def test_row_sharded_step_matches_oracle_emulated_ranks(cuda_device, world, adve
         assert int(t.local("GQ", r).count_nonzero().item()) == 0 and int(t.local("HQ", r).count_nonzero().item()) == 0
 
 
+@pytest.mark.parametrize("adver", [0, 1])
+def test_sharded_trainer_pipeline_single_rank(cuda_device, adver):
+    """ShardedTrainer's pipeline (side-stream preparation per sub-chunk, ready events, two alternating workspaces, calls
+    shorter than steps_per_call) on one rank (G = 1: no collective): five calls against the oracle."""
+    from apr_b200.distributed import ShardedTables, ShardedTrainer
+    rng = np.random.RandomState(40 + adver)
+    U, I, d, S, B = 2000, 1200, 64, 11, 1024
+    P, Q, u, i, j = _problem(rng, U, I, d, S, B)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 1.0, 0.5
+    rP, rQ, raP, raQ, rstats = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, adver)
+    dev = cuda_device
+    t = ShardedTables(U, I, d, B, dev, world=1, rank=0, symmetric=False)
+    t.load_full("P", _dev(P, torch.float32, dev))
+    t.load_full("Q", _dev(Q, torch.float32, dev))
+    t.load_full("accP", torch.full((U, d), 0.1, device=dev))
+    t.load_full("accQ", torch.full((I, d), 0.1, device=dev))
+    tr = ShardedTrainer(t, 3, B)
+    for s0 in (0, 3, 6, 9):                                # 3 + 3 + 3 + 2 steps
+        s1 = min(S, s0 + 3)
+        host = s0 == 3                                      # one call fed from pinned host memory
+        loc = [torch.from_numpy(x[s0:s1]).pin_memory() if host else _dev(x[s0:s1], torch.int32, dev) for x in (u, i, j)]
+        tr.train_steps(*loc, lr, reg, reg_adv, eps, adver)
+    tr.synchronize()
+    tr.check()
+    _close(t.gather_full("P", U).cpu().numpy(), rP)
+    _close(t.gather_full("Q", I).cpu().numpy(), rQ)
+    _close(t.gather_full("accP", U).cpu().numpy(), raP)
+    _close(t.gather_full("accQ", I).cpu().numpy(), raQ)
+
+
 @pytest.mark.timeout(900)
 def test_full_size_config4_step_matches_oracle_on_touched_rows(cuda_device):
     """BASELINE.json configs[3] at FULL size (10M users x 2M items, d=128, 65 536 triples per step): two APR steps on the

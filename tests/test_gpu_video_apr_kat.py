@@ -85,15 +85,19 @@ def test_video_bpr_to_apr_phase_switch_matches_reference_log(cuda_device):
 
     rel = lambda got, want: abs(got - want) / want
     # the BPR plateau the adversarial phase starts from
-    assert rel(p980, LOG_980[2]) < 0.04 and rel(q980, LOG_980[3]) < 0.04
-    assert abs(hr980 - LOG_980[0]) < 0.015 and abs(nd980 - LOG_980[1]) < 0.006
+    # (measured on a B200, round 2: 605.50 / 543.62, HR 0.2372, NDCG 0.0661 -- within 0.3 % of the logged norms)
+    assert rel(p980, LOG_980[2]) < 0.02 and rel(q980, LOG_980[3]) < 0.02
+    assert abs(hr980 - LOG_980[0]) < 0.01 and abs(nd980 - LOG_980[1]) < 0.005
     # first adversarial epoch: accuracy on its own batches saturates, the norms jump by an order of magnitude more than
     # a BPR epoch moves them (logged +10.8 / +18.8 against +0.07 / +0.055 per BPR epoch)
     assert prev_acc > 0.999 and post_acc > 0.9995
-    assert 0.5 * 10.8 < p1000 - p999 < 1.6 * 10.8
-    assert 0.5 * 18.8 < q1000 - q999 < 1.6 * 18.8
-    assert abs(hr1000 - LOG_1000[0]) < 0.015
+    # (measured: +10.96 / +18.22, |P| 617.71, |Q| 562.84)
+    assert 0.7 * 10.8 < p1000 - p999 < 1.3 * 10.8
+    assert 0.7 * 18.8 < q1000 - q999 < 1.3 * 18.8
+    assert rel(p1000, LOG_1000[2]) < 0.02 and rel(q1000, LOG_1000[3]) < 0.02
+    assert abs(hr1000 - LOG_1000[0]) < 0.01
     # twenty epochs later
-    assert rel(p1020, LOG_1020[2]) < 0.04 and rel(q1020, LOG_1020[3]) < 0.04
-    assert abs(hr1020 - LOG_1020[0]) < 0.015 and abs(nd1020 - LOG_1020[1]) < 0.006
+    # (measured: 675.40 / 627.15, HR 0.2446, NDCG 0.0673)
+    assert rel(p1020, LOG_1020[2]) < 0.02 and rel(q1020, LOG_1020[3]) < 0.02
+    assert abs(hr1020 - LOG_1020[0]) < 0.01 and abs(nd1020 - LOG_1020[1]) < 0.005
     assert hr1020 > hr980                                      # the adversarial phase lifts HR@100 above the BPR plateau
