@@ -213,7 +213,7 @@ def main_sharded(args):
     import torch.distributed as dist
 
     from apr_b200 import engine
-    from apr_b200.distributed import ShardedTables, train_steps_sharded
+    from apr_b200.distributed import ShardedTables, ShardedTrainer
 
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ.get("RANK", "0"))
@@ -232,36 +232,33 @@ def main_sharded(args):
     torch.cuda.synchronize()
     dist.barrier()
     rng = np.random.default_rng(2019 + rank)
-    CH = max(1, min(64, (1 << 22) // Bg))
-    ws = engine.TrainWorkspace(CH, Bg, d, dev)
-    aux = torch.cuda.Stream()
+    CH = max(2, min(32, (1 << 23) // Bg))      # steps per call of the pipelined driver (two workspaces of CH steps each)
+    trainer = ShardedTrainer(t, CH, Bl)
     hp = (CFG["lr"], CFG["reg"], CFG["reg_adv"], CFG["eps"], 1)
 
-    def global_chunk(n, host=None):
-        """local triples [n, Bl] -> all_gather -> global [n, Bg] on every rank"""
-        loc = host if host is not None else synth_triples(rng, n, Bl, U, I)
-        outs = []
-        for x in loc:
-            xl = (torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) if host is not None
-                  else torch.from_numpy(x).to(dev))
-            g = torch.empty((world, n, Bl), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(g, xl.contiguous())
-            outs.append(g.permute(1, 0, 2).reshape(n, Bg).contiguous())
-        return outs
+    def local_chunk(n):
+        """this rank's triples of n steps, resident in HBM (the trainer all_gathers them into the global batches)"""
+        return [torch.from_numpy(x).to(dev) for x in synth_triples(rng, n, Bl, U, I)]
 
     def run_chunk(u, i, j, stats=None):
-        train_steps_sharded(t, u, i, j, *hp, ws, aux_stream=aux, stats=stats)
+        trainer.train_steps(u, i, j, *hp, stats=stats)
 
-    done = 0
-    while done < W:
-        n = min(CH, W - done)
-        run_chunk(*global_chunk(n))
-        done += n
     chunks, left = [], K
     while left > 0:
         n = min(CH, left)
-        chunks.append(global_chunk(n))
+        chunks.append(local_chunk(n))
         left -= n
+    done = 0
+    while done < W:
+        n = min(CH, W - done)
+        run_chunk(*local_chunk(n))
+        done += n
+    for n in sorted({c[0].shape[0] for c in chunks}):      # every call shape of the timed region has run once
+        run_chunk(*local_chunk(n))
+        done += n
+    warmup_run = done
+    trainer.synchronize()
+    trainer.check()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -273,23 +270,33 @@ def main_sharded(args):
     for c in chunks:
         run_chunk(*c)
     ev1.record()
-    torch.cuda.synchronize()
+    trainer.synchronize()
     dist.barrier()
+    trainer.check()
     ms_t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
     clocks = sampler.stop() if rank == 0 else None
     value = K * Bg / (ms * 1e-3)
     # algorithmic bytes of the global steps (same index arrays on every rank)
-    cnt = ws.unique_counts(chunks[-1][0].shape[0]).astype(np.int64)
+    last_ws = trainer.ws[(trainer.calls - 1) & 1]
+    cnt = last_ws.unique_counts(chunks[-1][0].shape[0]).astype(np.int64)
     bytes_step = float(16 * d * cnt.sum() + 12 * Bg * cnt.shape[0]) / cnt.shape[0]
     achieved = bytes_step * K / (ms * 1e-3) / 1e9
+    # NVLink bytes per step and GPU of this exchange pattern: every item row a rank touches whose owner is another rank
+    # crosses the link twice (w + acc in, w + acc out), 4 d bytes per row and direction pair
+    remote = (world - 1) / world
+    nvl_dir = float(cnt[:, 1].mean()) / world * remote * 2 * 4 * d      # bytes per direction per GPU per step (lower bound)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak * world, "unit": "GB/s",
                 "frac": achieved / (hbm_peak * world), "traffic": None, "peak_kind": peak_kind,
-                "kernel": "fast_kernel + general_stage_kernel over NVLink-peer-mapped row shards",
-                "note": "aggregate over %d GPUs; (G-1)/G of the row traffic crosses NVLink (770 GB/s/dir/GPU measured)" % world}
-    # e2e: pinned host batches on every rank -> per chunk H2D -> all_gather -> sharded steps; D2H of the per-step loss
-    Ke = min(K, 4 * CH)
+                "kernel": "fast_kernel + pair_kernel + general_stage_kernel over NVLink-peer-mapped row shards",
+                "nvlink_gb_s_per_direction_per_gpu": nvl_dir / (ms / K * 1e-3) / 1e9,
+                "note": "aggregate over %d GPUs, whole step (index preparation, exchange and barriers included); (G-1)/G of "
+                        "the item-row traffic crosses NVLink: nvlink_* = unique item rows / G x (G-1)/G x (w + acc) per "
+                        "direction, against 900 GB/s nominal" % world}
+    # e2e: pinned host batches on every rank -> H2D + all_gather on the trainer's side stream -> sharded steps; D2H of the
+    # per-step loss
+    Ke = min(max(K, 8 * CH), 16 * CH)
     host = [torch.from_numpy(x).pin_memory() for x in synth_triples(rng, Ke, Bl, U, I)]
     stats = torch.zeros((Ke, 2), dtype=torch.float32, device=dev)
 
@@ -297,36 +304,34 @@ def main_sharded(args):
         stats.zero_()
         for s0 in range(0, Ke, CH):
             n = min(CH, Ke - s0)
-            outs = []
-            for x in host:
-                xl = x[s0:s0 + n].to(dev, non_blocking=True)
-                g = torch.empty((world, n, Bl), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(g, xl)
-                outs.append(g.permute(1, 0, 2).reshape(n, Bg).contiguous())
-            run_chunk(*outs, stats=stats[s0:s0 + n])
+            run_chunk(*[x[s0:s0 + n] for x in host], stats=stats[s0:s0 + n])
         dist.all_reduce(stats)
         return stats.cpu()
 
     e2e_pass()
-    torch.cuda.synchronize()
+    trainer.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
     e2e_pass()
-    torch.cuda.synchronize()
+    trainer.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    trainer.check()
     e2e = {"value": Ke * Bg / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": 12 * Bl, "d2h_bytes_per_step": 8,
-           "steps": Ke, "api": "distributed.train_steps_sharded(host batches per rank)"}
+           "steps": Ke, "api": "distributed.ShardedTrainer.train_steps(pinned host batches per rank)"}
     cfgd = workload_config(args)
     cfgd.update({"batch_per_step": Bg, "batch_per_gpu": Bl, "parallelism": "row-sharded tables over %d GPUs (NVLink peer "
                  "loads/stores/REDs inside the kernels), data-parallel over triples" % world,
-                 "step_mode": "fast kernel || pair kernel || general stages, 3 cross-rank barriers per step"})
+                 "step_mode": "fast kernel || pair kernel || general stages, 3 cross-rank barriers per step; index preparation "
+                              "+ one packed broadcast per sub-chunk pipelined on a side stream (ShardedTrainer)",
+                 "steps_per_call": CH})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfgd, "roofline": roofline, "e2e": e2e, "gpu_launches": K * 8 + 5 * len(chunks), "clocks": clocks}   # per step: fast, pair, 3 stages, 3 barriers
+            "config": cfgd, "roofline": roofline, "e2e": e2e, "gpu_launches": K * 8 + 5 * len(chunks), "clocks": clocks,   # per step: fast, pair, 3 stages, 3 barriers
+            "warmup_steps_run": warmup_run}
     # ---- second headline metric at N GPUs: item-sharded full-rank evaluation (BASELINE.json configs[4]) ----------
     if not args.no_eval and args.eval_users > 0:
-        del t, ws
+        del t, trainer, last_ws
         torch.cuda.empty_cache()
         _, tc_peak, _ = peaks()
         try:
@@ -426,11 +431,13 @@ def main_single(args):
         sc = max(1, min(S, (48 << 20) // ((max(32, 2 * p2) + max(32, 4 * p2)) * 8)))
         prep = 5 if pairs_on else 4      # insert, compact, scatter, [pair detection], pack
         step = 5 if pairs_on else 4      # fast kernel, [pair kernel], three general stages
-        nsub, left, n = 0, S, min(2, sc)          # sub-chunks of 2, 4, 8, ... sc steps (apr_train_steps)
+        nsub, nadv, left, n = 0, 0, S, min(2, sc)    # sub-chunks of 2, 4, 8, ... sc steps (apr_train_steps)
         while left > 0:
-            nsub, left, n = nsub + 1, left - min(left, n), min(sc, 2 * n)
-        # graph replay adds one cursor-advance node per group of 8/4/2/1 steps and one cursor-set launch per sub-chunk
-        return prep * nsub + (nsub if args.mode in (1, 2) else step * S + S // 8 + bin(S % 8).count("1") + nsub)
+            ns = min(left, n)
+            nsub, left, n = nsub + 1, left - ns, min(sc, 2 * n)
+            nadv += ns // 32 + bin(ns % 32).count("1")     # graph launches of 32/16/8/4/2/1 steps: one cursor-advance node each
+        graphs = B >= int(os.environ.get("APR_GRAPH_MIN_BATCH", "1024")) and os.environ.get("APR_GRAPH", "1") != "0"
+        return prep * nsub + (nsub if args.mode in (1, 2) else step * S + ((nadv + 1) if graphs else 0))
     launches = sum(n_launches(c[0].shape[0]) for c in chunks)
 
     # ---- roofline of the dominant kernel(s): the embedding step kernels, index preparation excluded -------
@@ -466,7 +473,8 @@ def main_single(args):
                 "bytes_per_step_model": bytes_step, "ms_per_step_kernel": ms_run / steps_roof}
 
     # ---- e2e: public API with HOST batches; H2D of ids and D2H of the per-step loss inside the region ------
-    Ke = min(K, 4 * CH)
+    # (at least 256 steps: a host-timed region of 20 steps = 2 ms measures the host's launch jitter, not the path)
+    Ke = min(max(K, 256), 4 * CH)
     # the steps' inputs wait in pinned host memory (bench contract); Session.train_steps streams them chunk by chunk
     hu, hi, hj = [torch.from_numpy(x).pin_memory() for x in synth_triples(rng, Ke, B, U, I)]
     stats = torch.zeros((Ke, 2), dtype=torch.float32, device=dev)
