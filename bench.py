@@ -610,7 +610,60 @@ def bench_variants(torch, engine, sess, model, args, hp, rng, dev):
     hp = hp_apr
     out = {"batch_sweep_uniform": sweep, "best_batch": best["batch"], "zipf_1.05_items": z, "bpr_step": bpr}
     out["sampler_epoch"] = bench_sampler(torch, engine, U, I, args.batch, dev)
+    # the other embedding sizes of BASELINE.json's configs (d = 64: configs[0-1]; d = 256: configs[4]) on the same
+    # 10M x 2M tables, each with its own roofline object (kernel-only and whole-step, like the headline line)
+    for dv in (64, 256):
+        if dv != d:
+            try:
+                out["dim_%d" % dv] = bench_dim_variant(torch, engine, args, hp_apr, rng, dev, dv)
+            except Exception as e:
+                out["dim_%d" % dv] = {"error": repr(e)}
     return out
+
+
+def bench_dim_variant(torch, engine, args, hp, rng, dev, d, steps=512):
+    """The headline measurement at another embedding size: device-resident ids, `steps` timed steps after a same-shape
+    warm-up (whole step: index preparation + step kernels), then the step kernels alone on prepared chunks."""
+    U, I, B = args.users, args.items, args.batch
+    hbm_peak, _, peak_kind = peaks()
+    P = torch.empty((U, d), dtype=torch.float32, device=dev)
+    Q = torch.empty((I, d), dtype=torch.float32, device=dev)
+    engine.init_truncated_normal(P, 0.01, 2019, 0)
+    engine.init_truncated_normal(Q, 0.01, 2019, 1)
+    aP, aQ = torch.full_like(P, 0.1), torch.full_like(Q, 0.1)
+    CH = max(1, min(256, (1 << 22) // B))
+    ws = engine.TrainWorkspace(CH, B, d, dev)
+    chunks = [[torch.from_numpy(x).to(dev) for x in synth_triples(rng, CH, B, U, I)] for _ in range(max(1, steps // CH) + 1)]
+    engine.train_steps(P, Q, aP, aQ, *chunks[0], *hp, ws, mode=args.mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for c in chunks[1:]:
+        engine.train_steps(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
+    e1.record()
+    torch.cuda.synchronize()
+    n = (len(chunks) - 1) * CH
+    ms_step = e0.elapsed_time(e1) / n
+    c = chunks[-1]
+    engine.train_prepare(P, Q, *c, ws)
+    engine.train_run(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    engine.train_run(P, Q, aP, aQ, *c, *hp, ws, mode=args.mode)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_kernel = k0.elapsed_time(k1) / CH
+    cnt = ws.unique_counts(CH).astype(np.int64)
+    bytes_step = float(16 * d * cnt.sum() + 12 * B * CH) / CH
+    res = {"d": d, "batch": B, "steps": n, "ms_per_step": ms_step, "triples_per_s": B / (ms_step * 1e-3),
+           "roofline": {"bound": "hbm", "achieved": bytes_step / (ms_kernel * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_step / (ms_kernel * 1e-3) / 1e9 / hbm_peak, "frac_kind": "kernel-only (apr_train_run)",
+                        "whole_step_achieved": bytes_step / (ms_step * 1e-3) / 1e9,
+                        "whole_step_frac": bytes_step / (ms_step * 1e-3) / 1e9 / hbm_peak, "traffic": measured_traffic(B, d, args.mode),
+                        "peak_kind": peak_kind, "bytes_per_step_model": bytes_step, "ms_per_step_kernel": ms_kernel}}
+    del P, Q, aP, aQ, ws, chunks
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_sampler(torch, engine, U, I, B, dev, pairs=1 << 26):
