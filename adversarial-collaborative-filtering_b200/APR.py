@@ -218,6 +218,8 @@ class MF:
 # ---------------------------------------------------------------------------------------------------------
 def sampling(dataset):
     """APR.py:30-36: the (u, i) keys of trainMatrix in insertion order."""
+    if hasattr(dataset, "device_pairs"):       # DeviceDataset (N1): the pair list already lives on the GPU
+        return dataset.device_pairs()
     if hasattr(dataset.trainMatrix, "pairs"):
         u, i = dataset.trainMatrix.pairs()
     else:
@@ -255,13 +257,19 @@ def shuffle(samples, batch_size, dataset, model, epoch: Optional[int] = None, ra
     model.shuffle_count += 1
     dev = model.device
     u_h, i_h = samples
-    u_h = np.asarray(u_h, dtype=np.int32) if not isinstance(u_h, np.ndarray) else u_h
-    i_h = np.asarray(i_h, dtype=np.int32) if not isinstance(i_h, np.ndarray) else i_h
-    pu = _cached_device("pairs_u", u_h, torch.int32, dev)
-    pi = _cached_device("pairs_i", i_h, torch.int32, dev)
-    ptr_h, idx_h = dataset.train_csr()
-    ptr = _cached_device("csr_ptr", ptr_h, torch.int64, dev)
-    idx = _cached_device("csr_idx", idx_h, torch.int32, dev)
+    if isinstance(u_h, torch.Tensor) and u_h.is_cuda:          # DeviceDataset: nothing to upload
+        pu, pi = u_h, i_h
+    else:
+        u_h = np.asarray(u_h, dtype=np.int32) if not isinstance(u_h, np.ndarray) else u_h
+        i_h = np.asarray(i_h, dtype=np.int32) if not isinstance(i_h, np.ndarray) else i_h
+        pu = _cached_device("pairs_u", u_h, torch.int32, dev)
+        pi = _cached_device("pairs_i", i_h, torch.int32, dev)
+    if hasattr(dataset, "device_train_csr"):
+        ptr, idx = dataset.device_train_csr()
+    else:
+        ptr_h, idx_h = dataset.train_csr()
+        ptr = _cached_device("csr_ptr", ptr_h, torch.int64, dev)
+        idx = _cached_device("csr_idx", idx_h, torch.int32, dev)
     u, i, ud, j, err = engine.sample_epoch(pu, pi, batch_size, dataset.num_items, ptr, idx, model.seed, epoch, model.dns,
                                            rank=rank, world=world,
                                            fork_workers=getattr(model, "fork_workers", 0) if fork_workers is None else fork_workers)

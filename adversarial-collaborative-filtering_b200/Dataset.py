@@ -204,3 +204,116 @@ class ArrayDataset(_DatasetBase):
         self.testRatings = [[int(a), int(b)] for a, b in zip(np.asarray(test_u).tolist(), np.asarray(test_i).tolist())]
         self.testNegatives = test_negatives
         self._csr = None
+
+
+class DeviceDataset(_DatasetBase):
+    """N1: ``OriginalDataset`` / ``HeDataset`` semantics with the parsing, de-duplication and CSR
+    construction done on the GPU (csrc/loader.cu): the file is read once into pinned memory, parsed by one thread per
+    line, the ``sampling`` pair list, the trainList rows (incl. the reference's cursor quirk) and the sorted
+    CSR come out of scans / radix sorts on the device and STAY there -- ``APR.sampling`` / ``APR.shuffle`` /
+    ``utils.init_eval_model`` pick the device tensors up directly, so no per-line Python runs between the file and the
+    first training step.  The reference's host attributes (``trainMatrix``, ``trainList``, ``testRatings``,
+    ``testNegatives``) are materialised lazily, only if somebody asks for them.
+
+    A train file that is not sorted by uid falls back to the host cursor for the trainList rows (the two-scan form of the
+    cursor holds for sorted files, which is what process_data.py:30-51 writes)."""
+
+    def __init__(self, path: str, reproduce_quirk: bool = True, negatives: bool = False, device=None):
+        import torch
+
+        from . import engine
+        self.reproduce_quirk = reproduce_quirk
+        self.device = engine.require_cuda() if device is None else device
+        u, i, r = engine.parse_rating_text(engine._file_to_device(path + ".train.rating", self.device))
+        self._du, self._di, self._dr = u, i, r
+        self.num_users = int(u.max().item()) + 1 if u.numel() else 1
+        self.num_items = int(i.max().item()) + 1 if i.numel() else 1
+        self._pairs = engine.unique_pairs_device(u, i, r)
+        row, is_sorted = engine.train_rows(u, reproduce_quirk)
+        if reproduce_quirk and not is_sorted:
+            lists = load_training_file_as_list(u.cpu().numpy().astype(np.int64), i.cpu().numpy().astype(np.int64), True)
+            row = torch.from_numpy(np.repeat(np.arange(len(lists), dtype=np.int32), [len(l) for l in lists])).to(self.device)
+        self._row = row
+        self._n_lists = int(row.max().item()) + 1 if row.numel() else 1
+        self._csr_dev = engine.build_csr_device(row, i, self._n_lists)
+        tu, ti, _ = engine.parse_rating_text(engine._file_to_device(path + ".test.rating", self.device))
+        self._test_u, self._test_i = tu, ti
+        self._neg_dev = engine.parse_negative_text(engine._file_to_device(path + ".test.negative", self.device)) if negatives else None
+        self._csr = None
+        self._host = {}
+
+    # ---- device views (what the CUDA path consumes) ----
+    def device_pairs(self):
+        return self._pairs
+
+    def device_train_csr(self):
+        return self._csr_dev
+
+    def device_eval_exclusion(self):
+        """Sorted CSR of trainList[u] united with {test item} for u in range(num_users) (utils.py:200-215)."""
+        import torch
+
+        from . import engine
+        keep = self._row < self.num_users
+        rows = torch.cat([self._row[keep], torch.arange(self.num_users, dtype=torch.int32, device=self.device)])
+        items = torch.cat([self._di[keep], self.device_test_items()])
+        return engine.build_csr_device(rows.contiguous(), items.contiguous(), self.num_users)
+
+    def device_test_items(self):
+        """test item of user u = testRatings[u][1] (the file holds one row per user in uid order, App. C)."""
+        if self._test_i.numel() < self.num_users:
+            raise ValueError("the test file has fewer rows than there are users")
+        return self._test_i[:self.num_users].contiguous()
+
+    # ---- the reference's host attributes, on demand ----
+    def _h(self, name, fn):
+        if name not in self._host:
+            self._host[name] = fn()
+        return self._host[name]
+
+    @property
+    def _train_u(self):
+        return self._h("u", lambda: self._du.cpu().numpy().astype(np.int64))
+
+    @property
+    def _train_i(self):
+        return self._h("i", lambda: self._di.cpu().numpy().astype(np.int64))
+
+    @property
+    def _train_r(self):
+        return self._h("r", lambda: self._dr.cpu().numpy())
+
+    @property
+    def trainMatrix(self):
+        keep = self._train_r > 0
+        return self._h("m", lambda: InteractionMatrix(self._train_u[keep], self._train_i[keep], (self.num_users, self.num_items)))
+
+    @property
+    def trainList(self):
+        def build():
+            row = self._row.cpu().numpy()
+            cut = np.flatnonzero(np.diff(row)) + 1
+            parts = np.split(self._train_i, cut)
+            lists = [[] for _ in range(self._n_lists)]
+            for r, p in zip(row[np.concatenate([[0], cut])].tolist() if row.size else [], parts):
+                lists[r] = lists[r] + p.tolist()
+            return lists
+        return self._h("l", build)
+
+    @property
+    def testRatings(self):
+        return self._h("t", lambda: [[int(a), int(b)] for a, b in zip(self._test_u.cpu().tolist(), self._test_i.cpu().tolist())])
+
+    @property
+    def testNegatives(self):
+        if self._neg_dev is None:
+            return None
+        def build():
+            ptr, idx = self._neg_dev[0].cpu().numpy(), self._neg_dev[1].cpu().numpy()
+            return [idx[ptr[k]:ptr[k + 1]].tolist() for k in range(ptr.size - 1)]
+        return self._h("n", build)
+
+    def train_csr(self):
+        if self._csr is None:
+            self._csr = (self._csr_dev[0].cpu().numpy(), self._csr_dev[1].cpu().numpy())
+        return self._csr

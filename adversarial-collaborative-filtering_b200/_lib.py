@@ -15,7 +15,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libapr_b200.so")
-SOURCES = ["api.cu", "train.cu", "sampler.cu", "eval.cu", "eval_tc.cu"]
+SOURCES = ["api.cu", "train.cu", "sampler.cu", "eval.cu", "eval_tc.cu", "loader.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -127,6 +127,12 @@ _SIGNATURES = {
     "apr_topk_merge": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "apr_eval_tc_timing": (ctypes.c_int, [c_int32, POINTER(c_float)]),
     "apr_sum_squares": (ctypes.c_int, [_P, c_int64, _P, _P]),
+    "apr_loader_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "apr_tsv_count_lines": (ctypes.c_int, [_P, c_int64, _P, c_int64, POINTER(c_int64), _P]),
+    "apr_tsv_parse": (ctypes.c_int, [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "apr_loader_train_rows": (ctypes.c_int, [_P, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
+    "apr_loader_csr": (ctypes.c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P]),
+    "apr_loader_unique_pairs": (ctypes.c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())

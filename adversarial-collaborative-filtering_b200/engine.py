@@ -393,3 +393,104 @@ def sum_squares(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(1, dtype=torch.float64, device=x.device)
     _lib.check(_lib.lib().apr_sum_squares(_ptr(x, torch.float32), x.numel(), _ptr(out), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# N1: device-side data loader (csrc/loader.cu)
+# ---------------------------------------------------------------------------------------------------------
+def _file_to_device(filename: str, device) -> torch.Tensor:
+    """One read() of the file into pinned memory, one H2D copy."""
+    size = __import__("os").path.getsize(filename)
+    host = torch.empty(max(size, 1), dtype=torch.uint8).pin_memory()
+    with open(filename, "rb") as f:
+        f.readinto(host.numpy())
+    return host[:size].to(device, non_blocking=True) if size else torch.zeros(0, dtype=torch.uint8, device=device)
+
+
+def _loader_ws(n_bytes: int, max_lines: int, device) -> torch.Tensor:
+    return torch.empty(_lib.lib().apr_loader_workspace_bytes(n_bytes, max_lines), dtype=torch.uint8, device=device)
+
+
+def parse_rating_text(text: torch.Tensor):
+    """uint8 device tensor holding a `*.rating` TSV -> (uid int32[n], iid int32[n], rating float32[n]) on the device."""
+    dev, nb = text.device, text.numel()
+    if nb == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z.clone(), torch.zeros(0, dtype=torch.float32, device=dev)
+    ws = _loader_ws(nb, 0, dev)
+    n = ctypes.c_int64(0)
+    _lib.check(_lib.lib().apr_tsv_count_lines(text.data_ptr(), nb, ws.data_ptr(), ws.numel(), ctypes.byref(n), _stream()))
+    n = int(n.value)
+    u = torch.empty(n, dtype=torch.int32, device=dev)
+    i = torch.empty(n, dtype=torch.int32, device=dev)
+    r = torch.empty(n, dtype=torch.float32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    if n:
+        _lib.check(_lib.lib().apr_tsv_parse(text.data_ptr(), nb, ws.data_ptr(), n, 0, _ptr(u), _ptr(i), _ptr(r), 0, 0, 0, _ptr(err),
+                                            _stream()))
+        if int(err.item()):
+            raise ValueError("malformed rating file (uid / iid must be non-negative integers, rating a decimal number)")
+    return u, i, r
+
+
+def parse_negative_text(text: torch.Tensor):
+    """He-format `.test.negative` text -> CSR (ptr int64[n+1], idx int32) of the ids after the first tab of every line."""
+    dev, nb = text.device, text.numel()
+    ws = _loader_ws(nb, 0, dev)
+    n = ctypes.c_int64(0)
+    _lib.check(_lib.lib().apr_tsv_count_lines(text.data_ptr(), nb, ws.data_ptr(), ws.numel(), ctypes.byref(n), _stream()))
+    n = int(n.value)
+    cnt = torch.zeros(n, dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().apr_tsv_parse(text.data_ptr(), nb, ws.data_ptr(), n, 1, 0, 0, 0, _ptr(cnt), 0, 0, _ptr(err), _stream()))
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    idx = torch.empty(int(ptr[-1].item()), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().apr_tsv_parse(text.data_ptr(), nb, ws.data_ptr(), n, 2, 0, 0, 0, 0, _ptr(ptr), _ptr(idx) if idx.numel() else 0,
+                                        _ptr(err), _stream()))
+    if int(err.item()):
+        raise ValueError("malformed negatives file")
+    return ptr, idx
+
+
+def train_rows(u: torch.Tensor, quirk: bool = True):
+    """trainList row of every train line (Dataset.py:306-325) -> (row int32[n], file_is_uid_sorted)."""
+    n = u.numel()
+    row = torch.empty(n, dtype=torch.int32, device=u.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=u.device)
+    if n:
+        ws = _loader_ws(0, n, u.device)
+        _lib.check(_lib.lib().apr_loader_train_rows(_ptr(u, torch.int32), n, int(bool(quirk)), _ptr(row), _ptr(flag), ws.data_ptr(),
+                                                    ws.numel(), _stream()))
+    return row, int(flag.item()) == 0
+
+
+def build_csr_device(row: torch.Tensor, item: torch.Tensor, n_rows: int):
+    """Sorted, de-duplicated CSR of (row, item) on the device -> (ptr int64[n_rows+1], idx int32[nnz])."""
+    n = row.numel()
+    dev = row.device
+    ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    if n == 0:
+        return ptr, torch.zeros(0, dtype=torch.int32, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _loader_ws(0, n, dev)
+    _lib.check(_lib.lib().apr_loader_csr(_ptr(row, torch.int32), _ptr(item, torch.int32), n, n_rows, _ptr(ptr), _ptr(idx), _ptr(nu),
+                                         ws.data_ptr(), ws.numel(), _stream()))
+    return ptr, idx[:int(nu.item())].clone()
+
+
+def unique_pairs_device(u: torch.Tensor, i: torch.Tensor, rating: torch.Tensor):
+    """(u, i) of the lines with rating > 0, duplicates collapsed onto the first occurrence, in file order (APR.py:30-36)."""
+    n = u.numel()
+    dev = u.device
+    if n == 0:
+        return u.clone(), i.clone()
+    ou = torch.empty(n, dtype=torch.int32, device=dev)
+    oi = torch.empty(n, dtype=torch.int32, device=dev)
+    m = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _loader_ws(0, n, dev)
+    _lib.check(_lib.lib().apr_loader_unique_pairs(_ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(rating, torch.float32), n, _ptr(ou),
+                                                  _ptr(oi), _ptr(m), ws.data_ptr(), ws.numel(), _stream()))
+    k = int(m.item())
+    return ou[:k].clone(), oi[:k].clone()

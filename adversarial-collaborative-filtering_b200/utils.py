@@ -227,9 +227,14 @@ def init_eval_model(dataset, args):
     """utils.py:178-218.  eval_mode "all": candidates = range(num_items) - trainList[u] - {test} + [test];
     "sample": 100 x random.choice(train iid column) with random.seed(2019) per user, rejecting train/test items."""
     num_users = dataset.num_users
+    mode = getattr(args, "eval_mode", "all")
+    if mode == "all" and hasattr(dataset, "device_eval_exclusion"):
+        # DeviceDataset (N1): the exclusion CSR is built on the GPU (sort + unique), no per-user Python
+        ptr, idx = dataset.device_eval_exclusion()
+        return EvalInputs("all", np.arange(num_users, dtype=np.int32), dataset.device_test_items().cpu().numpy(),
+                          dataset.num_items, excl_ptr=ptr.cpu().numpy(), excl_idx=idx.cpu().numpy())
     test = np.asarray([dataset.testRatings[u][1] for u in range(num_users)], dtype=np.int32)
     users = np.arange(num_users, dtype=np.int32)
-    mode = getattr(args, "eval_mode", "all")
     train_list = dataset.trainList
     if mode == "sample":
         iid = np.asarray(dataset.iid_column)

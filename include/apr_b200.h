@@ -253,6 +253,36 @@ int apr_topk_merge(const int32_t* in_ids, const float* in_scores, int32_t n_user
  * (-1 if none).  Not thread-safe; leave disabled in production. */
 int apr_eval_tc_timing(int32_t enable, float* gemm_ms_out);
 
+/* ---- N1: device-side data loader (csrc/loader.cu).  `text` = the bytes of a `*.rating` TSV file
+ *      ("uid \t iid \t rating \t timestamp", Dataset.py:278-304, App. C) or of a He-format `.test.negative` file
+ *      ("(u,i) \t n1 ... \t n99", Dataset.py:161-172) in DEVICE memory.  All functions use a caller workspace of
+ *      apr_loader_workspace_bytes(n_bytes, max_lines) bytes.
+ *      apr_tsv_count_lines  non-empty lines -> *n_lines_host (synchronises); leaves the per-block line bases in the
+ *                           workspace for apr_tsv_parse (same text, same workspace).
+ *      apr_tsv_parse        mode 0: columns uid / iid / rating (1.0 when the column is missing) [max_lines];
+ *                           mode 1: ids per negatives line -> tok_count; mode 2: the ids -> neg_idx at neg_ptr[line].
+ *                           *err_flag: bit 0 malformed field, bit 1 more lines than max_lines.
+ *      apr_loader_train_rows  the reference's trainList row of every line (Dataset.py:306-325): quirk != 0 reproduces
+ *                           its cursor that advances by at most one user per line as two prefix scans, valid
+ *                           for a uid-sorted file (*unsorted_flag is set otherwise: use the host cursor); quirk == 0: row = uid.
+ *      apr_loader_csr       sorted, de-duplicated CSR of (row, item): trainList membership structure (APR.py:77,
+ *                           utils.py:211) or the evaluation exclusion lists.
+ *      apr_loader_unique_pairs  keys of the dok trainMatrix in insertion order (rating > 0, duplicates collapsed onto the
+ *                           first occurrence): the (u, i) list `sampling` enumerates (APR.py:30-36). */
+int64_t apr_loader_workspace_bytes(int64_t n_bytes, int64_t max_lines);
+int apr_tsv_count_lines(const char* text, int64_t n_bytes, void* workspace, int64_t workspace_bytes, int64_t* n_lines_host,
+                        apr_stream_t stream);
+int apr_tsv_parse(const char* text, int64_t n_bytes, const void* workspace, int64_t max_lines, int32_t mode, int32_t* out_u,
+                  int32_t* out_i, float* out_r, int64_t* tok_count, const int64_t* neg_ptr, int32_t* neg_idx,
+                  int32_t* err_flag, apr_stream_t stream);
+int apr_loader_train_rows(const int32_t* u, int64_t n, int32_t quirk, int32_t* row, int32_t* unsorted_flag, void* workspace,
+                          int64_t workspace_bytes, apr_stream_t stream);
+int apr_loader_csr(const int32_t* row, const int32_t* item, int64_t n, int64_t rows, int64_t* ptr, int32_t* idx,
+                   int64_t* n_unique_dev, void* workspace, int64_t workspace_bytes, apr_stream_t stream);
+int apr_loader_unique_pairs(const int32_t* u, const int32_t* i, const float* rating, int64_t n, int32_t* out_u,
+                            int32_t* out_i, int64_t* n_pairs_dev, void* workspace, int64_t workspace_bytes,
+                            apr_stream_t stream);
+
 /* ---- K11: np.linalg.norm(embedding_P) of utils.py:92-97: *out (device double) = sum of squares. */
 int apr_sum_squares(const float* x, int64_t n, double* out, apr_stream_t stream);
 

@@ -153,3 +153,25 @@ def test_cli_defaults_match_reference():
 def test_build_sorted_csr():
     ptr, idx = build_sorted_csr([[3, 1, 3], [], [2]])
     assert ptr.tolist() == [0, 2, 2, 3] and idx.tolist() == [1, 3, 2]
+
+
+def test_trainlist_cursor_closed_form_equals_the_sequential_cursor():
+    """csrc/loader.cu computes the reference's trainList row of line k (Dataset.py:316-320: a cursor that advances by at
+    most one user per line and never passes the line's uid) as min(k + 1, k + prefix_min(uid_j - j)) -- valid for
+    uid-sorted files.  Checked against the sequential cursor on random sorted sequences with gaps and repeats."""
+    rng = np.random.RandomState(0)
+
+    def sequential(a):
+        c, out = 0, []
+        for x in a:
+            if c < x:
+                c += 1
+            out.append(c)
+        return np.asarray(out)
+
+    for _ in range(5000):
+        n = rng.randint(1, 60)
+        a = np.sort(rng.randint(0, rng.randint(1, 40), n))
+        k = np.arange(n)
+        closed = np.minimum(k + 1, k + np.minimum.accumulate(a - k))
+        assert np.array_equal(closed, sequential(a)), a
