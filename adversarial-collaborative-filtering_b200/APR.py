@@ -202,14 +202,34 @@ class MF:
         return fn
 
     def restore_weights(self, ckpt_dir: str) -> bool:
+        """tf.train.get_checkpoint_state + saver.restore (APR.py:226-230).  Returns False -- the caller then keeps the
+        fresh initialisation, as the reference does -- when the directory holds no checkpoint of THIS format (e.g. it was
+        written by the reference's TF Saver: index/data files, not .npz).  A checkpoint whose tables do
+        not have this model's shapes (APR.MF has num_users+1 / num_items+1 rows, evaluation_adv.MF exactly num_users /
+        num_items) is an error, not a silent partial restore."""
         state = os.path.join(ckpt_dir, "checkpoint")
         if not os.path.exists(state):
             return False
         with open(state) as f:
-            name = f.readline().split('"')[1]
-        z = np.load(os.path.join(ckpt_dir, name))
+            parts = f.readline().split('"')
+        if len(parts) < 2:
+            return False
+        fn = os.path.join(ckpt_dir, parts[1])
+        if not fn.endswith(".npz") or not os.path.exists(fn):
+            logging.warning("checkpoint %s is not an apr_b200 .npz checkpoint (TensorFlow Saver files cannot be read here): "
+                            "continuing from the initialisation", fn)
+            return False
+        z = np.load(fn)
+        for key, table in (("embedding_P", self.embedding_P), ("embedding_Q", self.embedding_Q)):
+            if key not in z.files:
+                raise ValueError("checkpoint %s has no array %r" % (fn, key))
+            if tuple(z[key].shape) != tuple(table.shape):
+                raise ValueError("checkpoint %s: %s has shape %s, the model expects %s (APR.MF tables carry one extra row, "
+                                 "evaluation_adv.MF tables do not)" % (fn, key, tuple(z[key].shape), tuple(table.shape)))
         self.embedding_P.copy_(torch.from_numpy(z["embedding_P"]))
         self.embedding_Q.copy_(torch.from_numpy(z["embedding_Q"]))
+        engine.touch(self.embedding_P)
+        engine.touch(self.embedding_Q)
         return True
 
 

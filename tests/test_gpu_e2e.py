@@ -49,6 +49,11 @@ def _oracle_epoch(ds, P, Q, aP, aQ, B, seed, epoch, lr, reg, reg_adv, eps, adver
 
 
 def test_epoch_drivers_match_oracle(cuda_device):
+    """What is bounded: per epoch, TEACHER-FORCED -- the oracle's tables are the GPU's at every epoch start, so each
+    comparison bounds the drift over ONE epoch of sequential steps (DRIFT_RTOL of max|table|); sampled triples are
+    bit-identical; metrics come from exact positions on the GPU's own tables.  A free-running multi-epoch APR trajectory
+    is not comparable in fp32 (chaotic map); tests/test_gpu_ml1m_shape.py bounds 97-step windows at
+    the reference's default scale and tests/test_gpu_video_apr_kat.py the 1 021-epoch statistics."""
     from apr_b200.APR import MF, Session, sampling, shuffle
     from apr_b200.Dataset import ArrayDataset
     from apr_b200.utils import evaluate, init_eval_model, training_batch, training_loss_acc
