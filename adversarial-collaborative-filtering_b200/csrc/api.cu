@@ -25,6 +25,10 @@ static bool context_init(DeviceContext& a) {
          cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
          cudaStreamCreateWithPriority(&a.pair_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
          cudaStreamCreateWithFlags(&a.capture_stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&a.gen_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&a.fast_lo_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&a.pair_lo_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+         cudaEventCreateWithFlags(&a.join3, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&a.join2, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess &&
@@ -37,8 +41,10 @@ static void context_free(DeviceContext* a) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   }
   for (auto e : a->prep_done) cudaEventDestroy(e);
-  for (cudaStream_t s : {a->capture_stream, a->fast_stream, a->pair_stream, a->prep_stream}) if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t e : {a->fork, a->join, a->join2, a->entry, a->tc_ev[0], a->tc_ev[1]}) if (e) cudaEventDestroy(e);
+  for (cudaStream_t s : {a->capture_stream, a->fast_stream, a->pair_stream, a->prep_stream, a->gen_stream, a->fast_lo_stream,
+                         a->pair_lo_stream})
+    if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : {a->fork, a->join, a->join2, a->join3, a->entry, a->tc_ev[0], a->tc_ev[1]}) if (e) cudaEventDestroy(e);
   delete a;
 }
 

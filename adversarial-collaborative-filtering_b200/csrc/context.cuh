@@ -34,7 +34,10 @@ struct DeviceContext {
   cudaStream_t fast_stream = nullptr;     // fast-path kernels
   cudaStream_t pair_stream = nullptr;     // pair work units
   cudaStream_t prep_stream = nullptr;     // index preparation, pipelined one sub-chunk ahead of the step kernels
-  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, entry = nullptr;
+  // "general path first" variant (narrow rows: the chain of general stages, not the fast kernel, is the critical path)
+  cudaStream_t gen_stream = nullptr;      // general stages at the HIGHEST priority
+  cudaStream_t fast_lo_stream = nullptr, pair_lo_stream = nullptr;   // fast / pair kernels at the lowest
+  cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr, join3 = nullptr, entry = nullptr;
   std::vector<cudaEvent_t> prep_done;
   std::vector<GraphEntry> graphs;
   unsigned long long graph_clock = 0;

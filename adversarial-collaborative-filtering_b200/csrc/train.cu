@@ -1466,21 +1466,39 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
     }
     const bool pairs = V == 1 && c.npair != nullptr;
     const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
+    // Which path gets the SM slots first.  Wide rows: the fast kernel is the critical path, so it (and the pair kernel)
+    // run at the highest stream priority and the general stages take what is left.  APR_GEN_PRIO=1 (default for rows of
+    // <= APR_GEN_PRIO_MAX_D floats) turns that around: the three dependent general launches run on a highest-priority
+    // stream, fast and pair kernels at the lowest -- with narrow rows the general chain is as long as the fast kernel and
+    // must not wait for the pair kernel's blocks to free registers.
+    static const int gen_prio = env_int("APR_GEN_PRIO", -1), gen_prio_max_d = env_int("APR_GEN_PRIO_MAX_D", 0);
+    const bool gen_first = gen_prio > 0 || (gen_prio < 0 && c.d <= gen_prio_max_d);
+    cudaStream_t fs = gen_first ? ax.fast_lo_stream : ax.fast_stream;
+    cudaStream_t ps = gen_first ? ax.pair_lo_stream : ax.pair_stream;
     // the launches of steps [s0, s1) with context cc, forked from / joined to `main`
     auto issue_steps = [&](const StepCtx& cc, cudaStream_t main, int s0, int s1) -> int {
+      cudaStream_t gs = gen_first ? ax.gen_stream : main;
       for (int s = s0; s < s1; ++s) {
         APR_CUDA_CHECK(cudaEventRecord(ax.fork, main));
-        APR_CUDA_CHECK(cudaStreamWaitEvent(ax.fast_stream, ax.fork, 0));
-        fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, ax.fast_stream>>>(cc, s);
-        APR_CUDA_CHECK(cudaEventRecord(ax.join, ax.fast_stream));
-        if (pairs) {
-          APR_CUDA_CHECK(cudaStreamWaitEvent(ax.pair_stream, ax.fork, 0));
-          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ax.pair_stream>>>(cc, s);
-          APR_CUDA_CHECK(cudaEventRecord(ax.join2, ax.pair_stream));
+        if (gen_first) {
+          APR_CUDA_CHECK(cudaStreamWaitEvent(gs, ax.fork, 0));
+          if (cc.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, gs>>>(cc, s, 0);
         }
-        if (cc.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 0);
-        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 1);
-        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, main>>>(cc, s, 2);
+        APR_CUDA_CHECK(cudaStreamWaitEvent(fs, ax.fork, 0));
+        fast_kernel<G, V, FULL><<<grid_fast, kThreads, 0, fs>>>(cc, s);
+        APR_CUDA_CHECK(cudaEventRecord(ax.join, fs));
+        if (pairs) {
+          APR_CUDA_CHECK(cudaStreamWaitEvent(ps, ax.fork, 0));
+          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ps>>>(cc, s);
+          APR_CUDA_CHECK(cudaEventRecord(ax.join2, ps));
+        }
+        if (!gen_first && cc.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, gs>>>(cc, s, 0);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, gs>>>(cc, s, 1);
+        general_stage_kernel<G, V><<<grid_gen, kThreads, 0, gs>>>(cc, s, 2);
+        if (gen_first) {
+          APR_CUDA_CHECK(cudaEventRecord(ax.join3, gs));
+          APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join3, 0));
+        }
         APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join, 0));
         if (pairs) APR_CUDA_CHECK(cudaStreamWaitEvent(main, ax.join2, 0));
       }
