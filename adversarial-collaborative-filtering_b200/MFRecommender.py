@@ -76,6 +76,28 @@ class BPRRecommender(Recommender):
     def rank(self, users, items):
         return self.mf.predict(users, items)
 
+    def rank_all(self, users, item_lo=0, item_hi=None):
+        """N4: `all_rating` of IRGAN.py:36-39 / APL.py:205-211 -- every item's score for each listed user, [n, items]."""
+        u = torch.as_tensor(np.asarray(users).reshape(-1), dtype=torch.int32).to(self.mf.device)
+        return engine.score_all_items(self.mf.embedding_P, self.mf.embedding_Q, u, item_lo, item_hi).cpu().numpy()
+
+    def recommend(self, users, k, exclude_ptr=None, exclude_idx=None):
+        """Top-k item ids per user over the whole catalogue on the tensor cores (score desc, ties to the smaller id);
+        ``exclude_*`` = sorted CSR of items to leave out (e.g. the train items)."""
+        dev = self.mf.device
+        u = torch.as_tensor(np.asarray(users).reshape(-1), dtype=torch.int32).to(dev)
+        n = u.numel()
+        if exclude_ptr is None:
+            exclude_ptr, exclude_idx = np.zeros(n + 1, np.int64), np.zeros(0, np.int32)
+        ptr = torch.as_tensor(np.asarray(exclude_ptr), dtype=torch.int64).to(dev)
+        idx = torch.as_tensor(np.asarray(exclude_idx), dtype=torch.int32).to(dev)
+        spos = torch.full((n,), 3.0e38, dtype=torch.float32, device=dev)   # no held-out item here: a finite score nothing reaches
+        _, ids, sc = engine.eval_fullrank(self.mf.embedding_P, self.mf.embedding_Q, u, torch.zeros(n, dtype=torch.int32, device=dev),
+                                          0, self.iNum, ptr, idx, k, exact=True) if not engine.tc_supported(self.dim) or self.iNum < 1024 \
+            else engine.eval_fullrank_tc(self.mf.embedding_P, self.mf.embedding_Q, u, None, 0, self.iNum, ptr, idx, check=False,
+                                         k_top=k, spos=spos)[:3]
+        return ids.cpu().numpy(), sc.cpu().numpy()
+
     def rank_batched(self, users_items):
         """Scores for many (user, candidate list) pairs in one launch (used by apr_b200.evaluation)."""
         lens = [len(it) for _, it in users_items]

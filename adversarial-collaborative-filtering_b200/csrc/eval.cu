@@ -30,6 +30,30 @@ score_pairs_kernel(const float* __restrict__ P, const float* __restrict__ Q, int
     scores[t] = score_chain(P + int64_t(users[t]) * d, Q + int64_t(items[t]) * d, d);
 }
 
+// N4: the all-item scorer `all_rating = u . Q^T` of IRGAN.py:36-39 / APL.py:205-211 for a batch of users:
+// out[k, c - item_lo] = score(users[k], c) with the pinned fma chain.  One CTA per (user, 1024-item slab); the user row
+// sits in shared memory, every thread walks the rows of its items with 128-bit loads.  Dense output: meant for the
+// per-user `rank` of the Recommender plug-ins (a few users at a time), not for full evaluation (that never writes scores).
+__global__ void __launch_bounds__(256)
+score_all_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users, int item_lo,
+                 int item_hi, float* __restrict__ out) {
+  extern __shared__ float sp[];
+  const int k = blockIdx.y;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) sp[e] = P[int64_t(users[k]) * d + e];
+  __syncthreads();
+  const int n_items = item_hi - item_lo;
+  for (int c = blockIdx.x * 1024 + threadIdx.x; c < min(n_items, (int(blockIdx.x) + 1) * 1024); c += blockDim.x) {
+    const float4* q4 = reinterpret_cast<const float4*>(Q + int64_t(item_lo + c) * d);
+    float acc = 0.f;
+    for (int e = 0; e < d / 4; ++e) {
+      const float4 b = __ldg(q4 + e);
+      acc = fmaf(sp[4 * e], b.x, acc); acc = fmaf(sp[4 * e + 1], b.y, acc);
+      acc = fmaf(sp[4 * e + 2], b.z, acc); acc = fmaf(sp[4 * e + 3], b.w, acc);
+    }
+    out[int64_t(k) * n_items + c] = acc;
+  }
+}
+
 // one CTA per user; candidate rows are read by 128-bit loads, the user row is staged in shared memory
 __global__ void __launch_bounds__(128)
 eval_candidates_kernel(const float* __restrict__ P, const float* __restrict__ Q, int d, const int32_t* __restrict__ users,
@@ -357,6 +381,18 @@ int apr_score_pairs(const float* P, const float* Q, int32_t d, const int32_t* us
   if (!P || !Q || !users || !items || !scores || n < 1 || !valid_dim(d)) return APR_E_ARG;
   if (!aligned16(P) || !aligned16(Q)) return APR_E_ALIGN;
   score_pairs_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, Q, d, users, items, n, scores);
+  APR_LAUNCH_CHECK();
+  return APR_OK;
+}
+
+int apr_score_all_items(const float* P, const float* Q, int32_t d, const int32_t* users, int32_t n_users, int32_t item_lo,
+                        int32_t item_hi, float* scores, apr_stream_t stream) {
+  if (!P || !Q || !users || !scores || n_users < 1 || n_users > 65535 || item_hi <= item_lo || item_lo < 0 || !valid_dim(d))
+    return APR_E_ARG;
+  if (!aligned16(P) || !aligned16(Q)) return APR_E_ALIGN;
+  const int slabs = (item_hi - item_lo + 1023) / 1024;
+  score_all_kernel<<<dim3(slabs, n_users), 256, size_t(d) * 4, static_cast<cudaStream_t>(stream)>>>(P, Q, d, users, item_lo, item_hi,
+                                                                                                   scores);
   APR_LAUNCH_CHECK();
   return APR_OK;
 }

@@ -248,6 +248,17 @@ def score_pairs(P, Q, users, items, q_row_offset: int = 0) -> torch.Tensor:
     return out
 
 
+def score_all_items(P, Q, users, item_lo: int = 0, item_hi: Optional[int] = None) -> torch.Tensor:
+    """N4: dense [n_users, item_hi - item_lo] scores u . Q^T in the pinned order (IRGAN.py:36-39 `all_rating`)."""
+    item_hi = Q.shape[0] if item_hi is None else item_hi
+    n = users.numel()
+    out = torch.empty((n, item_hi - item_lo), dtype=torch.float32, device=P.device)
+    if n:
+        _lib.check(_lib.lib().apr_score_all_items(_ptr(P, torch.float32), _ptr(Q, torch.float32), P.shape[1], _ptr(users, torch.int32),
+                                                  n, item_lo, item_hi, _ptr(out), _stream()))
+    return out
+
+
 def eval_candidates(P, Q, users, cand_ptr, cand_idx, want_scores: bool = False):
     n = users.numel()
     pos = torch.empty(n, dtype=torch.int32, device=P.device)

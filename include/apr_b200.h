@@ -182,6 +182,13 @@ int apr_loss_acc(const float* P, const float* Q, int32_t d, const int32_t* u, co
 int apr_score_pairs(const float* P, const float* Q, int32_t d, const int32_t* users, const int32_t* items, int64_t n,
                     float* scores, apr_stream_t stream);
 
+/* ---- N4: the all-item scorer `all_rating = u . Q^T` behind `rank` of IRGAN.py:36-39 / APL.py:205-211 /
+ *      SASRec.py:424-436: scores[k, c - item_lo] = <P[users[k]], Q[c]> for c in [item_lo, item_hi), pinned fma order.
+ *      Dense [n_users, item_hi - item_lo] output: for a few users at a time (n_users <= 65535); full evaluation uses
+ *      apr_eval_fullrank*, which never writes the score matrix. */
+int apr_score_all_items(const float* P, const float* Q, int32_t d, const int32_t* users, int32_t n_users, int32_t item_lo,
+                        int32_t item_hi, float* scores, apr_stream_t stream);
+
 /* ---- A10 / K8: _eval_by_user on explicit candidate lists, utils.py:244-254 and evaluation.py:114-128.
  *      User k has candidates cand_idx[cand_ptr[k] .. cand_ptr[k+1]) with the held-out item LAST;
  *      position[k] = #(score(neg) >= score(held-out)).  scores (nullable) receives every candidate score. */

@@ -70,3 +70,31 @@ def test_evaluation_module_batched_on_gpu(cuda_device):
     hits, ndcgs = evaluation.evaluate_model(r, test, negs, 10, 1)      # one launch for all users (rank_batched)
     ohits, ondcgs = O.evaluate_model_topk(P, Q, {u: test[u] for u in range(1, ds.num_users)}, negs, 10)
     assert hits == ohits and np.allclose(ndcgs, ondcgs)
+
+
+def test_all_item_scorer_and_recommend(cuda_device):
+    """N4: `all_rating = u . Q^T` (IRGAN.py:36-39, APL.py:205-211) bit-exact against the oracle's pinned score
+    order, and top-k recommendation over the whole catalogue (tensor-core path) == argsort of those scores with ties to
+    the smaller id and the excluded items left out."""
+    from apr_b200.MFRecommender import BPRRecommender
+    rng = np.random.RandomState(8)
+    U, I, d, K = 60, 2500, 64, 20
+    rec = BPRRecommender(U, I, d)
+    P = rec.mf.embedding_P.cpu().numpy() * 50
+    Q = rec.mf.embedding_Q.cpu().numpy() * 50
+    Q[77] = Q[5]                                               # a tie
+    rec.mf.embedding_P.copy_(torch.from_numpy(P)); rec.mf.embedding_Q.copy_(torch.from_numpy(Q))
+    users = np.asarray([3, 17, 59, 0], dtype=np.int32)
+    got = rec.rank_all(users)
+    want = np.stack([O.score_pairs(P, Q, np.full(I, u), np.arange(I)) for u in users])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    part = rec.rank_all(users, 100, 1500)
+    assert np.array_equal(part, got[:, 100:1500])
+    excl = [sorted(set(rng.randint(0, I, 15).tolist())) for _ in users]
+    ptr = np.concatenate([[0], np.cumsum([len(e) for e in excl])]).astype(np.int64)
+    ids, sc = rec.recommend(users, K, ptr, np.concatenate(excl).astype(np.int32))
+    for k, u in enumerate(users):
+        cand = np.setdiff1d(np.arange(I), excl[k])
+        order = cand[np.lexsort((cand, -want[k][cand].astype(np.float64)))][:K]
+        assert ids[k].tolist() == order.tolist()
+        assert np.array_equal(sc[k].view(np.uint32), want[k][order].view(np.uint32))
