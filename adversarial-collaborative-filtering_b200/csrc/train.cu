@@ -1466,15 +1466,15 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
     }
     const bool pairs = V == 1 && c.npair != nullptr;
     const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
-    // Which path gets the SM slots first.  Wide rows: the fast kernel is the critical path, so it (and the pair kernel)
-    // run at the highest stream priority and the general stages take what is left.  APR_GEN_PRIO=1 (default for rows of
-    // <= APR_GEN_PRIO_MAX_D floats) turns that around: the three dependent general launches run on a highest-priority
-    // stream, fast and pair kernels at the lowest -- with narrow rows the general chain is as long as the fast kernel and
-    // must not wait for the pair kernel's blocks to free registers.
-    static const int gen_prio = env_int("APR_GEN_PRIO", -1), gen_prio_max_d = env_int("APR_GEN_PRIO_MAX_D", 0);
-    const bool gen_first = gen_prio > 0 || (gen_prio < 0 && c.d <= gen_prio_max_d);
-    cudaStream_t fs = gen_first ? ax.fast_lo_stream : ax.fast_stream;
-    cudaStream_t ps = gen_first ? ax.pair_lo_stream : ax.pair_stream;
+    // Which path gets the SM slots first (experiments, APR_GEN_PRIO bit mask; default 0 = the fast and pair kernels run at
+    // the highest stream priority and the general stages, on the caller's stream, take what is left):
+    //   bit 0  the three dependent general launches run on a highest-priority stream of their own
+    //   bit 1  the fast kernel runs at the lowest priority        bit 2  the pair kernel runs at the lowest priority
+    // Measured (B=65536, kernel-only fraction): d=64  mask 0: 0.683, mask 7: 0.661;  d=128  mask 0: 0.821, mask 7: 0.790.
+    static const int gen_prio = env_int("APR_GEN_PRIO", 0);
+    const bool gen_first = (gen_prio & 1) != 0;
+    cudaStream_t fs = (gen_prio & 2) ? ax.fast_lo_stream : ax.fast_stream;
+    cudaStream_t ps = (gen_prio & 4) ? ax.pair_lo_stream : ax.pair_stream;
     // the launches of steps [s0, s1) with context cc, forked from / joined to `main`
     auto issue_steps = [&](const StepCtx& cc, cudaStream_t main, int s0, int s1) -> int {
       cudaStream_t gs = gen_first ? ax.gen_stream : main;
