@@ -1470,7 +1470,8 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
     // the highest stream priority and the general stages, on the caller's stream, take what is left):
     //   bit 0  the three dependent general launches run on a highest-priority stream of their own
     //   bit 1  the fast kernel runs at the lowest priority        bit 2  the pair kernel runs at the lowest priority
-    // Measured (B=65536, kernel-only fraction): d=64  mask 0: 0.683, mask 7: 0.661;  d=128  mask 0: 0.821, mask 7: 0.790.
+    // Measured (B=65536, kernel-only fraction): d=64  mask 0: 0.683, 4: 0.684, 1 / 5 / 7: 0.660-0.661;  d=128  mask 0:
+    // 0.821, 4: 0.821, 1 / 5 / 7: 0.789-0.791 -- the extra fork/join of a fourth stream costs more than the order buys.
     static const int gen_prio = env_int("APR_GEN_PRIO", 0);
     const bool gen_first = (gen_prio & 1) != 0;
     cudaStream_t fs = (gen_prio & 2) ? ax.fast_lo_stream : ax.fast_stream;

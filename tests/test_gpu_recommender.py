@@ -1,6 +1,7 @@
 """The Recommender plug-in surface (Recommender.py:3-27) on the CUDA engine."""
 import numpy as np
 import pytest
+import torch
 
 from oracle import apr_oracle as O
 
