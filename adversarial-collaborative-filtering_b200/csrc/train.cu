@@ -1662,7 +1662,9 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
   int32_t* tkey_i = at<int32_t>(ws, L.off_tkey_i);
   int32_t* tval_i = at<int32_t>(ws, L.off_tval_i);
   const int threads = 256;
-  static const int prep_bps = env_int("APR_PREP_BLOCKS", 16);
+  // resident preparation blocks per SM: the preparation must finish a sub-chunk faster than the steps consume one, or the
+  // step pipeline stalls (B=65536, d=128: 2 -> 638, 4 -> 723, 8 -> 758, 16 -> 762, 32 -> 768 M triples/s)
+  static const int prep_bps = env_int("APR_PREP_BLOCKS", 32);
   const int64_t cap = int64_t(sm_count()) * std::max(1, prep_bps);
   // table keys = -1, table values = 0
   APR_CUDA_CHECK(cudaMemsetAsync(tkey_u, 0xFF, size_t(int64_t(ns) * L.Tu * 4), st));
