@@ -489,6 +489,51 @@ def test_row_sharded_step_matches_oracle_emulated_ranks(cuda_device, world, adve
         assert int(t.local("GQ", r).count_nonzero().item()) == 0 and int(t.local("HQ", r).count_nonzero().item()) == 0
 
 
+def test_graph_cache_never_reinstantiates_after_first_sight(cuda_device):
+    """Round 1 re-instantiated its step graph whenever a call's step count differed from the previous one (a 20-step timed
+    call after a 5-step warm-up paid two cudaGraphInstantiate inside the timed region).  Now the first call of a
+    configuration builds the executable graphs of EVERY group size; any later step count replays them: the library's
+    instantiation counter must not move, and the results stay the oracle's."""
+    from apr_b200 import engine
+    rng = np.random.RandomState(77)
+    U, I, d, B = 5000, 3000, 64, 2048
+    S_all = 3 + 1 + 20 + 7 + 33
+    P, Q, u, i, j = _problem(rng, U, I, d, S_all, B)
+    lr, reg, reg_adv, eps = 0.05, 0.01, 1.0, 0.5
+    dev = cuda_device
+    tP, tQ = _dev(P, torch.float32, dev), _dev(Q, torch.float32, dev)
+    aP, aQ = torch.full_like(tP, 0.1), torch.full_like(tQ, 0.1)
+    ws = engine.TrainWorkspace(40, B, d, dev)
+    tu, ti, tj = _dev(u, torch.int32, dev), _dev(i, torch.int32, dev), _dev(j, torch.int32, dev)
+    s0, counts = 0, []
+    for n in (3, 1, 20, 7, 33):                      # odd step counts: every group size 32/16/8/4/2/1 gets replayed
+        engine.train_steps(tP, tQ, aP, aQ, tu[s0:s0 + n], ti[s0:s0 + n], tj[s0:s0 + n], lr, reg, reg_adv, eps, 1, ws, mode=0)
+        torch.cuda.synchronize()
+        counts.append(engine.context_stats())
+        s0 += n
+    assert counts[0]["graph_launches"] > 0, "graph replay is off for this batch size"
+    for c in counts[1:]:
+        assert c["graph_instantiations"] == counts[0]["graph_instantiations"], counts
+        assert c["graph_updates"] == counts[0]["graph_updates"], counts
+    assert counts[-1]["graph_launches"] > counts[0]["graph_launches"]
+    # BPR on the same tables / workspace is a different configuration: it builds its own graphs once, then replays
+    engine.train_steps(tP, tQ, aP, aQ, tu[:5], ti[:5], tj[:5], lr, reg, reg_adv, eps, 0, ws, mode=0)
+    c_bpr = engine.context_stats()
+    engine.train_steps(tP, tQ, aP, aQ, tu[:9], ti[:9], tj[:9], lr, reg, reg_adv, eps, 0, ws, mode=0)
+    engine.train_steps(tP, tQ, aP, aQ, tu[:11], ti[:11], tj[:11], lr, reg, reg_adv, eps, 1, ws, mode=0)
+    assert engine.context_stats()["graph_instantiations"] == c_bpr["graph_instantiations"]
+    # and the arithmetic of the replayed steps is the oracle's (the APR part, before the extra calls: re-run it)
+    tP2, tQ2 = _dev(P, torch.float32, dev), _dev(Q, torch.float32, dev)
+    aP2, aQ2 = torch.full_like(tP2, 0.1), torch.full_like(tQ2, 0.1)
+    s0 = 0
+    for n in (3, 1, 20, 7, 33):
+        engine.train_steps(tP2, tQ2, aP2, aQ2, tu[s0:s0 + n], ti[s0:s0 + n], tj[s0:s0 + n], lr, reg, reg_adv, eps, 1, ws, mode=0)
+        s0 += n
+    rP, rQ, raP, raQ, _ = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, 1)
+    _close(tP2.cpu().numpy(), rP, 3e-5)              # 64 sequential APR steps: see DRIFT_RTOL in test_gpu_e2e.py
+    _close(tQ2.cpu().numpy(), rQ, 3e-5)
+
+
 @pytest.mark.parametrize("adver", [0, 1])
 def test_sharded_trainer_pipeline_single_rank(cuda_device, adver):
     """ShardedTrainer's pipeline (side-stream preparation per sub-chunk, ready events, two alternating workspaces, calls
