@@ -530,8 +530,8 @@ def test_graph_cache_never_reinstantiates_after_first_sight(cuda_device):
         engine.train_steps(tP2, tQ2, aP2, aQ2, tu[s0:s0 + n], ti[s0:s0 + n], tj[s0:s0 + n], lr, reg, reg_adv, eps, 1, ws, mode=0)
         s0 += n
     rP, rQ, raP, raQ, _ = _run_oracle_steps(P, Q, u, i, j, lr, reg, reg_adv, eps, 1)
-    _close(tP2.cpu().numpy(), rP, 3e-5)              # 64 sequential APR steps: see DRIFT_RTOL in test_gpu_e2e.py
-    _close(tQ2.cpu().numpy(), rQ, 3e-5)
+    _close(tP2.cpu().numpy(), rP, 1e-4)              # 64 sequential APR steps (drift bound as in tests/test_gpu_e2e.py;
+    _close(tQ2.cpu().numpy(), rQ, 1e-4)              # a wrong step index would be off by orders of magnitude more)
 
 
 @pytest.mark.parametrize("adver", [0, 1])
