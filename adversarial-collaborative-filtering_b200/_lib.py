@@ -110,7 +110,7 @@ _SIGNATURES = {
     "apr_train_steps_sharded": (ctypes.c_int, [POINTER(c_void_p)] * 7 + [c_int32, c_int32, c_int32, c_int32, c_int32,
                                                c_float, c_float, c_float, c_float, c_int32, _P, c_int64, _P, c_int32,
                                                c_int32, _P, _P]),
-    "apr_train_unique_counts": (ctypes.c_int, [_P, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
+    "apr_train_unique_counts": (ctypes.c_int, [_P, c_int64, c_int32, c_int32, c_int32, POINTER(c_int32), _P]),
     "apr_loss_acc": (ctypes.c_int, [_P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]),
     "apr_score_pairs": (ctypes.c_int, [_P, _P, c_int32, _P, _P, c_int64, _P, _P]),
     "apr_score_all_items": (ctypes.c_int, [_P, _P, c_int32, _P, c_int32, c_int32, c_int32, _P, _P]),

@@ -108,6 +108,27 @@ static TrainLayout make_layout(int S, int B, int d) {
   return L;
 }
 
+// The layout of a workspace is a function of its SIZE (and of batch, d), not of the step count of the call that uses it:
+// the capacity is the largest step count whose arrays fit, and a call of n <= capacity steps uses the first n step slots.
+// So every array keeps its address from call to call -- which is what lets an executable CUDA graph of the step be
+// replayed for calls of any length (the addresses are kernel parameters baked into its nodes).
+static bool layout_for_ws(int64_t ws_bytes, int B, int d, int steps_needed, TrainLayout& L) {
+  thread_local struct { int64_t bytes = -1; int B = 0, d = 0; TrainLayout L; } memo;
+  if (!(memo.bytes == ws_bytes && memo.B == B && memo.d == d)) {
+    if (make_layout(1, B, d).total > ws_bytes) return false;
+    int64_t lo = 1, hi = 2;                                  // layout(lo) fits; total is monotone in the step count
+    while (hi <= (int64_t(1) << 22) && make_layout(int(hi), B, d).total <= ws_bytes) { lo = hi; hi *= 2; }
+    while (lo + 1 < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (make_layout(int(mid), B, d).total <= ws_bytes) lo = mid; else hi = mid;
+    }
+    memo.bytes = ws_bytes; memo.B = B; memo.d = d;
+    memo.L = make_layout(int(lo), B, d);
+  }
+  L = memo.L;
+  return L.S >= steps_needed;
+}
+
 template <typename T>
 static inline T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
@@ -1718,13 +1739,8 @@ static int prepare_sub(const int32_t* u, const int32_t* i, const int32_t* j, con
   return APR_OK;
 }
 
-static int prepare_clear(const TrainLayout& L, void* ws, cudaStream_t st) {
-  // per-step counters and slow flags = 0
-  APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, L.off_ucnt), 0, size_t(L.off_seg_user - L.off_ucnt), st));
-  return APR_OK;
-}
-
-// the same for the steps [s0, s0+ns) only (other steps' arrays may already hold another rank's broadcast)
+// per-step counters and slow flags of the steps [s0, s0+ns) = 0 (other steps' arrays may hold another rank's broadcast, or
+// simply are not part of this call: the workspace may have room for many more steps than a call uses)
 static int prepare_clear_range(const TrainLayout& L, void* ws, int s0, int ns, cudaStream_t st) {
   const int64_t offs[7] = {L.off_ucnt, L.off_icnt, L.off_iall, L.off_nslow, L.off_nfast, L.off_tcursor, L.off_npair};
   for (int k = 0; k < 7; ++k) APR_CUDA_CHECK(cudaMemsetAsync(at<char>(ws, offs[k]) + int64_t(s0) * 4, 0, size_t(ns) * 4, st));
@@ -1735,9 +1751,9 @@ static int prepare_clear_range(const TrainLayout& L, void* ws, int s0, int ns, c
 
 static int prepare_impl(const int32_t* u, const int32_t* i, const int32_t* j, int S, int B, int d, int64_t rows_p,
                         int64_t rows_q, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
-  int rc = prepare_clear(L, ws, st);
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
+  int rc = prepare_clear_range(L, ws, 0, S, st);
   for (int s0 = 0; s0 < S && !rc; s0 += L.Sc)
     rc = prepare_sub(u, i, j, L, s0, std::min(L.Sc, S - s0), rows_p, rows_q, ws, st, pairs_enabled(d));
   return rc;
@@ -1786,7 +1802,7 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.Pb[0] = P; c.Qb[0] = Q; c.aPb[0] = accP; c.aQb[0] = accQ;
   c.GQb[0] = at<float>(ws, L.off_GQ); c.HQb[0] = at<float>(ws, L.off_HQ);
   c.nranks = 1; c.rank = 0; c.rshift = 0; c.only_stage = -1; c.cluster_sync = 0;
-  c.d = d; c.B = B; c.S = S;
+  c.d = d; c.B = B; c.S = L.S;
   c.lr = lr;
   // k = 2 reg (1 + [adver]) / (B d): the mean-regulariser is added once, or twice when adver (APR.py:153-154,163-165)
   c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
@@ -1821,8 +1837,8 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, adver);
   if (rc) return rc;
   if (mode < 0 || mode > 2) return APR_E_ARG;
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceContext* ctx = device_context();
   if (!ctx) return APR_E_CUDA;
@@ -1846,8 +1862,8 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, adver);
   if (rc) return rc;
   if (mode < 0 || mode > 2) return APR_E_ARG;
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceContext* ctx = device_context();
   if (!ctx) return APR_E_CUDA;
@@ -1857,7 +1873,7 @@ int apr_train_steps(float* P, float* Q, float* accP, float* accQ, int64_t rows_p
   // everything already enqueued on the caller's stream (producers of u,i,j; earlier steps reading the arrays) first
   APR_CUDA_CHECK(cudaEventRecord(ax.entry, st));
   APR_CUDA_CHECK(cudaStreamWaitEvent(ax.prep_stream, ax.entry, 0));
-  rc = prepare_clear(L, ws, ax.prep_stream);
+  rc = prepare_clear_range(L, ws, 0, S, ax.prep_stream);
   if (rc) return rc;
   // sub-chunks of 2, 4, 8, ... up to Sc steps: only the index preparation of the FIRST sub-chunk is exposed in front of
   // the step kernels (it cannot start before the previous call's steps have released the per-step arrays), so it is
@@ -1890,8 +1906,8 @@ int apr_train_steps_random(float* P, float* Q, float* accP, float* accQ, int64_t
                            float* stats, apr_stream_t stream) {
   int rc = check_train_args(P, Q, accP, accQ, rows_p, rows_q, d, u, i, j, S, B, ws, 1);
   if (rc) return rc;
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceContext* ctx = device_context();
   if (!ctx) return APR_E_CUDA;
@@ -1917,8 +1933,8 @@ int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j
   if (!u || !i || !j || !ws || S < 1 || B < 1 || rows_p < 1 || rows_q < 1 || !valid_dim(d)) return APR_E_ARG;
   if (s0 < 0 || ns < 1 || s0 + ns > S) return APR_E_ARG;
   if (!aligned16(ws)) return APR_E_ALIGN;
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = clear_counters ? prepare_clear_range(L, ws, s0, ns, st) : APR_OK;
   for (int a = s0; a < s0 + ns && !rc; a += L.Sc) rc = prepare_sub(u, i, j, L, a, std::min(L.Sc, s0 + ns - a), rows_p, rows_q, ws, st, pairs_enabled(d));
@@ -1934,8 +1950,8 @@ static int stage_sharded_impl(float* const* Pb, float* const* Qb, float* const* 
   if (adver < 0 || adver > 1) return APR_E_UNSUPPORTED;   // row-sharded tables: BPR and gradient-based APR only
   if (nranks < 1 || nranks > kMaxRanks || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return APR_E_ARG;
   if (S < 1 || B < 1 || !valid_dim(d) || step < 0 || step >= S || stage < 0 || stage > 4) return APR_E_ARG;
-  const TrainLayout L = make_layout(S, B, d);
-  if (ws_bytes < L.total) return APR_E_WORKSPACE;
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   DeviceContext* ctx = device_context();
   if (!ctx) return APR_E_CUDA;
   std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -1951,7 +1967,7 @@ static int stage_sharded_impl(float* const* Pb, float* const* Qb, float* const* 
   c.nranks = nranks; c.rank = rank;
   c.rshift = 0;
   while ((1 << c.rshift) < nranks) ++c.rshift;
-  c.d = d; c.B = B; c.S = S; c.lr = lr;
+  c.d = d; c.B = B; c.S = L.S; c.lr = lr;
   c.kreg = float(2.0 * double(reg) * (adver ? 2.0 : 1.0) / (double(B) * double(d)));
   c.reg_adv = reg_adv; c.eps = eps; c.adver = adver ? 1 : 0;
   c.plain_scale = 1.0f;
@@ -2107,9 +2123,11 @@ int apr_train_status(const void* ws, int32_t* flags_host, apr_stream_t stream) {
   return APR_OK;
 }
 
-int apr_train_unique_counts(const void* ws, int32_t S, int32_t B, int32_t d, int32_t* counts_host, apr_stream_t stream) {
+int apr_train_unique_counts(const void* ws, int64_t ws_bytes, int32_t S, int32_t B, int32_t d, int32_t* counts_host,
+                            apr_stream_t stream) {
   if (!ws || !counts_host || S < 1 || B < 1 || !valid_dim(d)) return APR_E_ARG;
-  const TrainLayout L = make_layout(S, B, d);
+  TrainLayout L;
+  if (!layout_for_ws(ws_bytes, B, d, S, L)) return APR_E_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* tmp = static_cast<int32_t*>(malloc(size_t(S) * 8 + 8));
   if (!tmp) return APR_E_ARG;

@@ -117,7 +117,7 @@ class TrainWorkspace:
         """[n_steps, 2] {unique users, unique items} of the last prepared chunk (synchronises).
         Raises if an out-of-range id was seen."""
         out = np.zeros((n_steps, 2), dtype=np.int32)
-        _lib.check(_lib.lib().apr_train_unique_counts(self.buf.data_ptr(), n_steps, self.batch, self.d,
+        _lib.check(_lib.lib().apr_train_unique_counts(self.buf.data_ptr(), self.nbytes, n_steps, self.batch, self.d,
                                                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _stream()))
         return out
 

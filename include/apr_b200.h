@@ -98,7 +98,11 @@ int apr_select_dns(const float* P, const float* Q, int32_t d, const int32_t* u_d
  *      u,i,j are [n_steps * batch].  accP/accQ are the Adagrad accumulators (same shape as P/Q, init 0.1).
  *      Delta never exists as a table: it lives in a per-step workspace of touched rows.
  *      The workspace must hold apr_train_workspace_bytes(n_steps, batch, d) bytes and must have been zeroed once
- *      with apr_train_workspace_init before first use (the kernels restore the zero invariant themselves).
+ *      with apr_train_workspace_init before first use (the kernels restore the zero invariant themselves).  Its internal
+ *      layout is a function of (workspace_bytes, batch, d) only -- capacity = the largest step count that fits -- so a
+ *      workspace sized for N steps serves calls of any n_steps <= N with the same array addresses (which is what lets
+ *      the executable CUDA graphs of the step be replayed for calls of any length); pass the same workspace_bytes to
+ *      every entry point that takes the workspace.
  *      stats (nullable) receives per step {sum softplus(-r) of the PLAIN forward, count(x > 0)} as float[2].
  *      mode: 0 = one kernel launch per phase (3 per APR step, 2 per BPR step);
  *            1 = one persistent cooperative kernel for all n_steps (grid barriers between phases);
@@ -140,8 +144,8 @@ int apr_train_run(float* P, float* Q, float* accP, float* accQ, int64_t rows_p, 
  * copies n_steps int32 pairs {unique users, unique items} to the HOST buffer; synchronises the stream.
  * Returns APR_E_ARG if any id seen by apr_train_prepare since apr_train_workspace_init was outside its table
  * (such ids are clamped to row 0 on the device instead of faulting). */
-int apr_train_unique_counts(const void* workspace, int32_t n_steps, int32_t batch, int32_t d, int32_t* counts_host,
-                            apr_stream_t stream);
+int apr_train_unique_counts(const void* workspace, int64_t workspace_bytes, int32_t n_steps, int32_t batch, int32_t d,
+                            int32_t* counts_host, apr_stream_t stream);
 
 /* ---- Row-sharded training over peer-mapped tables (multi-GPU drop-in for the same sess.run pair).
  *      Row r of a table lives on rank r % nranks at local row r / nranks (nranks in {1,2,4,8}); Pb/Qb/accPb/accQb are
@@ -151,6 +155,8 @@ int apr_train_unique_counts(const void* workspace, int32_t n_steps, int32_t batc
  *      apr_train_layout reports) and processes every nranks-th segment.  One call launches ONE stage of ONE step:
  *      stage 0,1,2 = general path, 3 = fast kernel, 4 = pair work units; the caller puts a cross-rank barrier after
  *      stages 0, 1 and after {2,3,4}.  apr_b200/distributed.py is that caller. */
+/* apr_train_layout: byte offsets of the index arrays inside a workspace of EXACTLY apr_train_workspace_bytes(n_steps,
+ * batch, d) bytes (the layout follows the workspace size, see apr_train_steps). */
 int apr_train_layout(int32_t n_steps, int32_t batch, int32_t d, int64_t* out13);
 int apr_train_prepare_range(const int32_t* u, const int32_t* i, const int32_t* j, int32_t n_steps, int32_t batch,
                             int32_t d, int64_t rows_p, int64_t rows_q, void* workspace, int64_t workspace_bytes,
