@@ -75,6 +75,57 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_sharded_table(rank, world, port, out):
+    """Every rank holds ONLY its rows of the item table: the held-out scores come from the owning rank through the
+    all_reduce of evaluate_item_sharded (x + 0 == x), exactly as on the GPU path (evaluate_item_sharded_cuda)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, Q, train, test, I = _case()
+    lo_r, hi_r = shard_bounds(I, world, rank, 128)
+    Q_local = Q[lo_r:hi_r].copy()                      # the only item rows this rank may touch
+
+    def held_out(lo, hi):
+        s = np.zeros(P.shape[0], np.float32)
+        for u in range(P.shape[0]):
+            if lo <= test[u] < hi:
+                s[u] = O.score_pairs(P, Q_local, [u], [test[u] - lo])[0]
+        return torch.from_numpy(s)
+
+    def eval_range(lo, hi, spos):
+        U = P.shape[0]
+        pos = np.zeros(U, np.int32)
+        ids = np.full((U, 5), -1, np.int32)
+        sc = np.full((U, 5), -np.inf, np.float32)
+        for u in range(U):
+            cands = [c for c in range(lo, hi) if c not in train[u] and c != test[u]]
+            if cands:
+                s = O.score_pairs(P, Q_local, np.full(len(cands), u), np.asarray(cands) - lo)
+                pos[u] = int((s >= spos[u].item()).sum())
+                order = np.lexsort((np.asarray(cands), -s.astype(np.float64)))[:5]
+                ids[u, :order.size] = np.asarray(cands)[order]
+                sc[u, :order.size] = s[order]
+        return torch.from_numpy(pos), torch.from_numpy(ids), torch.from_numpy(sc)
+
+    pos, ids, sc = evaluate_item_sharded(eval_range, I, k_top=5, held_out_scores=held_out)
+    if rank == 0:
+        torch.save((pos, ids, sc), out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_item_sharded_eval_with_sharded_item_table(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker_sharded_table, args=(2, port, out), nprocs=2, join=True)
+    pos, ids, sc = torch.load(out)
+    P, Q, train, test, I = _case()
+    wpos, wids, wsc = _oracle_range(P, Q, train, test, 0, I, 5)
+    assert torch.equal(pos, wpos) and torch.equal(ids, wids) and torch.equal(sc, wsc)
+
+
 @pytest.mark.timeout(300)
 def test_item_sharded_eval_equals_single_range(tmp_path):
     with socket.socket() as s:
