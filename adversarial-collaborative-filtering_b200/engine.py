@@ -308,6 +308,8 @@ def eval_tc_timing(enable: bool) -> float:
     return float(ms.value)
 
 
+EVAL_USER_TILE = 16384   # users per tensor-core evaluation call (larger user sets are tiled by eval_fullrank_tc)
+
 # grow-only evaluation workspace per device: keeping its address stable is what lets the library find the cached
 # item-operand image again on the next user tile (apr_eval_fullrank_tc_topk, q_version)
 _EVAL_WS = {}
@@ -357,6 +359,22 @@ def eval_fullrank_tc(P, Q, users, test_item, item_lo: int, item_hi: int, excl_pt
     dev = P.device
     if position is None:
         position = torch.zeros(n, dtype=torch.int32, device=dev)
+    if n > EVAL_USER_TILE:
+        # one library call takes a tile of the users (its per-CTA counter block and its (user, item) list are sized per
+        # call); the item-operand image is built once and reused by every tile
+        outs = []
+        for a0 in range(0, n, EVAL_USER_TILE):
+            sl = slice(a0, min(n, a0 + EVAL_USER_TILE))
+            sub_ptr = (excl_ptr[sl.start:sl.stop + 1] - excl_ptr[sl.start]).contiguous()
+            e0, e1 = int(excl_ptr[sl.start].item()), int(excl_ptr[sl.stop].item())
+            outs.append(eval_fullrank_tc(P, Q, users[sl].contiguous(), None if test_item is None else test_item[sl].contiguous(),
+                                         item_lo, item_hi, sub_ptr, excl_idx[e0:e1].contiguous(), position=position[sl],
+                                         check=check, k_top=k_top, cache_q=True,
+                                         spos=None if spos is None else spos[sl].contiguous(), q_row_offset=q_row_offset))
+        if k_top:
+            info = {k: sum(o[3][k] for o in outs) for k in outs[0][3]} if check else {"ambiguous": -1}
+            return position, torch.cat([o[1] for o in outs]), torch.cat([o[2] for o in outs]), info
+        return position, (sum(o[1] for o in outs) if check else -1)
     n_items = item_hi - item_lo
     if q_row_offset and (item_lo < q_row_offset or item_hi > q_row_offset + Q.shape[0]):
         raise ValueError("item range [%d, %d) is outside the local shard of Q" % (item_lo, item_hi))

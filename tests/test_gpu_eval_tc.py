@@ -157,3 +157,25 @@ def test_tc_q_image_cache_and_sharded_table(cuda_device):
     part_w, pi_w, _ = engine.eval_fullrank(tP, tQ, users, ttest, lo, hi, tptr, tidx, K, exact=True)
     part, pi, _, _ = engine.eval_fullrank_tc(tP, q_shard, users, None, lo, hi, tptr, tidx, k_top=K, spos=spos, q_row_offset=lo)
     assert torch.equal(part, part_w) and torch.equal(pi, pi_w)
+
+
+def test_tc_eval_tiles_large_user_sets(cuda_device, monkeypatch):
+    """More users than one library call takes: engine.eval_fullrank_tc tiles them (cached item image) and returns the same
+    positions / top-k as the exact kernel on the whole set."""
+    from apr_b200 import engine
+    from apr_b200.Dataset import build_sorted_csr
+    monkeypatch.setattr(engine, "EVAL_USER_TILE", 96)
+    U, I, d, K = 300, 3000, 64, 10
+    rng = np.random.RandomState(31)
+    P, Q, train, test = _case(rng, U, I, d, 1.0)
+    ptr, idx = build_sorted_csr([train[u] + [int(test[u])] for u in range(U)])
+    dev = cuda_device
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    args = [t(P, torch.float32), t(Q, torch.float32), t(np.arange(U, dtype=np.int32), torch.int32), t(test, torch.int32), 0, I,
+            t(ptr, torch.int64), t(idx, torch.int32)]
+    pos_e, ids_e, sc_e = engine.eval_fullrank(*args, K, exact=True)
+    pos_t, ids_t, sc_t, info = engine.eval_fullrank_tc(*args, k_top=K)
+    assert torch.equal(pos_t, pos_e) and torch.equal(ids_t, ids_e) and torch.equal(sc_t.view(torch.int32), sc_e.view(torch.int32))
+    pos_0, n_amb = engine.eval_fullrank_tc(*args)
+    assert torch.equal(pos_0, pos_e) and n_amb >= 0
+    engine.release_eval_workspace()
