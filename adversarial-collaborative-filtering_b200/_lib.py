@@ -15,7 +15,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libapr_b200.so")
-SOURCES = ["api.cu", "train.cu", "sampler.cu", "eval.cu", "eval_tc.cu", "loader.cu"]
+SOURCES = ["api.cu", "train.cu", "sampler.cu", "eval.cu", "eval_tc.cu", "loader.cu", "keras_mf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -128,6 +128,8 @@ _SIGNATURES = {
     "apr_topk_merge": (ctypes.c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "apr_eval_tc_timing": (ctypes.c_int, [c_int32, POINTER(c_float)]),
     "apr_sum_squares": (ctypes.c_int, [_P, c_int64, _P, _P]),
+    "apr_keras_step": (ctypes.c_int, [_P] * 8 + [c_int64, c_int64, c_int32, _P, _P, _P, _P, c_int32, c_int32, c_float, c_float,
+                                      c_float, c_int64, _P, _P]),
     "apr_loader_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "apr_tsv_count_lines": (ctypes.c_int, [_P, c_int64, _P, c_int64, POINTER(c_int64), _P]),
     "apr_tsv_parse": (ctypes.c_int, [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -523,3 +523,23 @@ def unique_pairs_device(u: torch.Tensor, i: torch.Tensor, rating: torch.Tensor):
                                                   _ptr(oi), _ptr(m), ws.data_ptr(), ws.numel(), _stream()))
     k = int(m.item())
     return ou[:k].clone(), oi[:k].clone()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# N3: Keras MatrixFactorization / BPR Recommender models (csrc/keras_mf.cu)
+# ---------------------------------------------------------------------------------------------------------
+def keras_step(P, Q, mP, vP, mQ, vQ, gP, gQ, u, i, j=None, y=None, lr=0.001, beta1=0.9, beta2=0.999, t=1,
+               loss_sum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One ``model.fit`` batch of MF.py (``y``: labels) or BPR.py (``j``: negative items) with Keras' dense Adam.
+    Returns the device double that accumulates the summed loss."""
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=P.device)
+    kind = 0 if y is not None else 1
+    _lib.check(_lib.lib().apr_keras_step(_ptr(P, torch.float32), _ptr(Q, torch.float32), _ptr(mP, torch.float32),
+                                         _ptr(vP, torch.float32), _ptr(mQ, torch.float32), _ptr(vQ, torch.float32),
+                                         _ptr(gP, torch.float32), _ptr(gQ, torch.float32), P.shape[0], Q.shape[0], P.shape[1],
+                                         _ptr(u, torch.int32), _ptr(i, torch.int32), _ptr(j, torch.int32), _ptr(y, torch.float32),
+                                         u.numel(), kind, float(lr), float(beta1), float(beta2), int(t), _ptr(loss_sum), _stream()))
+    touch(P)
+    touch(Q)
+    return loss_sum

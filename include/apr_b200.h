@@ -296,6 +296,18 @@ int apr_loader_unique_pairs(const int32_t* u, const int32_t* i, const float* rat
                             int32_t* out_i, int64_t* n_pairs_dev, void* workspace, int64_t workspace_bytes,
                             apr_stream_t stream);
 
+/* ---- N3: one training batch of the Keras Recommender models -- MF.py:7-59 `MatrixFactorization`
+ *      (loss_kind 0: binary_crossentropy of the RAW dot product clipped to [1e-7, 1 - 1e-7], MF.py:21-24; inputs users,
+ *      items, labels y) and BPR.py:23-102 `BPR` (loss_kind 1: mean of 1 - log sigmoid(<u,i> - <u,j>), BPR.py:11-21; inputs
+ *      users, positive items, negative items j) -- with Keras 2.2's Adam, which densifies the Embedding gradients: every
+ *      row's moments decay and every row moves at every batch.  mP/vP/mQ/vQ: Adam moments (zero-initialised, table
+ *      shapes); gP/gQ: dense gradient scratch of the table shapes, zero on entry and left zero; t: 1-based iteration;
+ *      *loss_sum (device double) += sum of the batch's per-instance losses.  Parity: Keras unpinned (oracle.keras_step). */
+int apr_keras_step(float* P, float* Q, float* mP, float* vP, float* mQ, float* vQ, float* gP, float* gQ, int64_t rows_p,
+                   int64_t rows_q, int32_t d, const int32_t* u, const int32_t* i, const int32_t* j, const float* y,
+                   int32_t n, int32_t loss_kind, float lr, float beta1, float beta2, int64_t t, double* loss_sum,
+                   apr_stream_t stream);
+
 /* ---- K11: np.linalg.norm(embedding_P) of utils.py:92-97: *out (device double) = sum of squares. */
 int apr_sum_squares(const float* x, int64_t n, double* out, apr_stream_t stream);
 

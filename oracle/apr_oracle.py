@@ -684,3 +684,45 @@ def legacy_fork_epoch(pairs_u, pairs_i, batch_size, num_items, train_sets, rng: 
                 jj = r.randint(num_items)
             J[s, b] = jj
     return U, I, J
+
+
+# ----------------------------------------------------------------------------------------------
+# N3: the Keras Recommender models (MF.py:7-59, BPR.py:23-102) -- parity unpinned (Keras / TF not installable)
+# ----------------------------------------------------------------------------------------------
+KERAS_EPS = 1e-7   # K.epsilon(): clip of binary_crossentropy and Adam's epsilon (Keras 2.2 defaults)
+
+
+def keras_step(P, Q, mP, vP, mQ, vQ, u, i, j=None, y=None, lr=0.001, b1=0.9, b2=0.999, t=1):
+    """One batch of ``model.fit`` for MF.py (``y`` given: binary_crossentropy(y, <u,i>) with the raw dot product clipped
+    to [1e-7, 1-1e-7], MF.py:21-24) or BPR.py (``j`` given: mean(1 - log sigmoid(<u,i> - <u,j>)), BPR.py:11-21), then
+    Keras 2.2's Adam on DENSIFIED Embedding gradients: lr_t = lr sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g;
+    v = b2 v + (1-b2) g^2; w -= lr_t m / (sqrt(v) + 1e-7) for EVERY row.  In place; returns the batch's summed loss."""
+    dt = P.dtype
+    u, i = np.asarray(u).reshape(-1), np.asarray(i).reshape(-1)
+    n = u.size
+    p, q = P[u], Q[i]
+    gP, gQ = np.zeros_like(P), np.zeros_like(Q)
+    if y is not None:
+        y = np.asarray(y, dtype=dt).reshape(-1)
+        pred = (p * q).sum(axis=1, dtype=dt)
+        ph = np.clip(pred, dt.type(KERAS_EPS), dt.type(1.0 - KERAS_EPS))
+        loss = -(y * np.log(ph) + (1 - y) * np.log(1 - ph))
+        inside = ((pred >= dt.type(KERAS_EPS)) & (pred <= dt.type(1.0 - KERAS_EPS))).astype(dt)
+        c = (inside * (-y / ph + (1 - y) / (1 - ph)) / dt.type(n)).astype(dt)
+        np.add.at(gP, u, c[:, None] * q)
+        np.add.at(gQ, i, c[:, None] * p)
+    else:
+        j = np.asarray(j).reshape(-1)
+        r = Q[j]
+        x = (p * q).sum(axis=1, dtype=dt) - (p * r).sum(axis=1, dtype=dt)
+        loss = 1.0 + _softplus(-x)
+        c = (-1.0 / (1.0 + np.exp(x)) / dt.type(n)).astype(dt)
+        np.add.at(gP, u, c[:, None] * (q - r))
+        np.add.at(gQ, i, c[:, None] * p)
+        np.add.at(gQ, j, -c[:, None] * p)
+    lr_t = dt.type(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    for W, M, V, g in ((P, mP, vP, gP), (Q, mQ, vQ, gQ)):
+        M[:] = dt.type(b1) * M + dt.type(1.0 - b1) * g
+        V[:] = dt.type(b2) * V + dt.type(1.0 - b2) * g * g
+        W -= lr_t * M / (np.sqrt(V) + dt.type(KERAS_EPS))
+    return float(loss.sum(dtype=np.float64))

@@ -99,3 +99,57 @@ def test_all_item_scorer_and_recommend(cuda_device):
         order = cand[np.lexsort((cand, -want[k][cand].astype(np.float64)))][:K]
         assert ids[k].tolist() == order.tolist()
         assert np.array_equal(sc[k].view(np.uint32), want[k][order].view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["mf", "bpr"])
+def test_keras_models_match_oracle(cuda_device, kind):
+    """N3: MF.py `MatrixFactorization` (BCE on the raw dot product) and BPR.py `BPR` (1 - log sigmoid) with
+    Keras' dense Adam: five batches through apr_keras_step against oracle.keras_step (every row moves at every batch)."""
+    from apr_b200 import engine
+    rng = np.random.RandomState(2)
+    U, I, d, n = 90, 70, 32, 200
+    P = rng.uniform(-0.05, 0.05, (U, d)).astype(np.float32)
+    Q = rng.uniform(-0.05, 0.05, (I, d)).astype(np.float32)
+    if kind == "mf":
+        P *= 8                                      # dot products inside (1e-7, 1): the clip passes gradient for some, not all
+        Q *= 8
+    dev = cuda_device
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    tP, tQ = t(P, torch.float32), t(Q, torch.float32)
+    st = [torch.zeros_like(x) for x in (tP, tP, tQ, tQ, tP, tQ)]
+    rP, rQ = P.copy(), Q.copy()
+    rs = [np.zeros_like(x) for x in (P, P, Q, Q)]
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+    want = 0.0
+    for step in range(1, 6):
+        u, i, j = rng.randint(0, U, n).astype(np.int32), rng.randint(0, I, n).astype(np.int32), rng.randint(0, I, n).astype(np.int32)
+        y = rng.randint(0, 2, n).astype(np.float32)
+        if kind == "mf":
+            want += O.keras_step(rP, rQ, *rs, u, i, y=y, t=step)
+            engine.keras_step(tP, tQ, *st, t(u, torch.int32), t(i, torch.int32), y=t(y, torch.float32), t=step, loss_sum=total)
+        else:
+            want += O.keras_step(rP, rQ, *rs, u, i, j=j, t=step)
+            engine.keras_step(tP, tQ, *st, t(u, torch.int32), t(i, torch.int32), j=t(j, torch.int32), t=step, loss_sum=total)
+    assert abs(float(total.item()) - want) <= 1e-5 * abs(want)
+    for got, ref in ((tP, rP), (tQ, rQ), (st[0], rs[0]), (st[1], rs[1]), (st[2], rs[2]), (st[3], rs[3])):
+        g = got.cpu().numpy()
+        assert np.abs(g - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-30), kind
+    assert int(st[4].count_nonzero().item()) == 0 and int(st[5].count_nonzero().item()) == 0     # gradient scratch left zero
+    assert np.abs(rP - P).min() > 0                                                               # dense Adam: every row moved
+
+
+def test_keras_recommender_surface(cuda_device):
+    from apr_b200.BPR import BPR
+    from apr_b200.MF import MatrixFactorization
+    rng = np.random.RandomState(4)
+    ds = _toy(rng)
+    for cls in (MatrixFactorization, BPR):
+        m = cls(ds.num_users, ds.num_items, 16)
+        x, y = m.get_train_instances(ds.trainMatrix)
+        assert len(x) == (2 if cls is MatrixFactorization else 3) and len(y) == len(x[0])
+        l0 = m.train(x, y, 64)
+        for _ in range(30):
+            l1 = m.train(x, y, 64)
+        assert np.isfinite(l0) and np.isfinite(l1) and l1 < l0            # the loss goes down
+        s = m.rank(np.asarray([1, 2, 3]), np.asarray([4, 5, 6]))
+        assert s.shape == (3,) and np.all(np.isfinite(s))

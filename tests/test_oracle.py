@@ -139,6 +139,37 @@ def test_given_delta_steps_match_torch_autograd(variant):
     assert np.allclose(Q, tQ.detach().numpy(), rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("kind", ["mf", "bpr"])
+def test_keras_step_gradients_match_torch_autograd(kind):
+    """N3: oracle.keras_step (MF.py:21-24 BCE on the clipped raw dot product / BPR.py:11-21 `1 - log sigmoid`): the loss
+    and, through the first Adam moments (m_1 = (1 - b1) g, v_1 = (1 - b2) g^2), the dense gradients equal torch autograd
+    of the loss as written; the update follows Keras 2.2's Adam formula (epsilon outside the bias correction)."""
+    rng = np.random.RandomState(0)
+    U, I, d, n = 30, 20, 8, 64
+    P = rng.uniform(-0.4, 0.4, (U, d))
+    Q = rng.uniform(-0.4, 0.4, (I, d))
+    u, i, j = rng.randint(0, U, n), rng.randint(0, I, n), rng.randint(0, I, n)
+    y = rng.randint(0, 2, n).astype(np.float64)
+    tP, tQ = torch.tensor(P, requires_grad=True), torch.tensor(Q, requires_grad=True)
+    tu, ti, tj = [torch.tensor(x, dtype=torch.long) for x in (u, i, j)]
+    if kind == "mf":
+        ph = (tP[tu] * tQ[ti]).sum(1).clamp(1e-7, 1 - 1e-7)
+        loss = -(torch.tensor(y) * ph.log() + (1 - torch.tensor(y)) * (1 - ph).log()).mean()
+    else:
+        x = (tP[tu] * tQ[ti]).sum(1) - (tP[tu] * tQ[tj]).sum(1)
+        loss = (1 - torch.nn.functional.logsigmoid(x)).mean()
+    gP, gQ = torch.autograd.grad(loss, [tP, tQ])
+    mP, vP, mQ, vQ = [np.zeros_like(a) for a in (P, P, Q, Q)]
+    P2, Q2 = P.copy(), Q.copy()
+    total = O.keras_step(P2, Q2, mP, vP, mQ, vQ, u, i, j=None if kind == "mf" else j, y=y if kind == "mf" else None, t=1)
+    assert abs(total / n - loss.item()) < 1e-12
+    assert np.allclose(mP, 0.1 * gP.numpy(), rtol=1e-9, atol=1e-15) and np.allclose(mQ, 0.1 * gQ.numpy(), rtol=1e-9, atol=1e-15)
+    assert np.allclose(vP, 0.001 * gP.numpy() ** 2, rtol=1e-9, atol=1e-18)
+    lr_t = 0.001 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    assert np.allclose(P2, P - lr_t * mP / (np.sqrt(vP) + 1e-7), rtol=1e-12, atol=0)
+    assert np.all(P2[np.setdiff1d(np.arange(U), u)] == P[np.setdiff1d(np.arange(U), u)])   # first step: untouched rows have g = 0
+
+
 def test_clip_blocks_gradient_outside_interval():
     P = np.array([[40.0, 0.0]], dtype=np.float64)
     Q = np.array([[0.0, 0.0], [3.0, 0.0]], dtype=np.float64)
