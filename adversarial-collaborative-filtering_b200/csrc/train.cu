@@ -519,8 +519,14 @@ __device__ __forceinline__ float* shard_row(float* const* base, int id, int d, c
 #define Q_ROW(c, id) shard_row((c).Qb, (id), (c).d, (c))
 #define AP_ROW(c, id) shard_row((c).aPb, (id), (c).d, (c))
 #define AQ_ROW(c, id) shard_row((c).aQb, (id), (c).d, (c))
-#define GQ_ROW(c, slot) shard_row((c).GQb, (slot), (c).d, (c))
-#define HQ_ROW(c, slot) shard_row((c).HQb, (slot), (c).d, (c))
+// APR_STEP_FLAGS bit 0 (TIMING EXPERIMENT ONLY, results are wrong): every access to the shared-item workspace goes to this
+// rank's own shard, i.e. the vector REDs / reads of G_Q, H_Q stop crossing NVLink -- isolates what they cost
+__device__ __forceinline__ float* slot_row(float* const* base, int slot, int d, const StepCtx& c) {
+  const int owner = (c.flags & 1) ? c.rank : (slot & (c.nranks - 1));
+  return base[owner] + int64_t(slot >> c.rshift) * d;
+}
+#define GQ_ROW(c, slot) slot_row((c).GQb, (slot), (c).d, (c))
+#define HQ_ROW(c, slot) slot_row((c).HQb, (slot), (c).d, (c))
 
 template <int G, int V>
 struct Row {
