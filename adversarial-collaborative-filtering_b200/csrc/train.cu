@@ -1148,7 +1148,7 @@ __device__ __forceinline__ unsigned group_mask() {
   StepStats st = {0.f, 0.f, stats != nullptr};
 
 template <int G, int V>
-__global__ void __launch_bounds__(kThreads) general_stage_kernel(StepCtx c, int s_param, int stage) {
+__global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : 1)) general_stage_kernel(StepCtx c, int s_param, int stage) {
   const int lane = threadIdx.x % G;
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
   const int ngroups = gridDim.x * (kThreads / G);
@@ -1175,8 +1175,8 @@ __global__ void __launch_bounds__(kThreads, (V == 1 ? 4 : (V == 2 ? 2 : 1))) fas
 template <int G, int V>
 __global__ void __launch_bounds__(kThreads, 2) pair_kernel(StepCtx c, int s_param) {
   const int lane = threadIdx.x % G;
-  const int gid = (blockIdx.x * kThreads + threadIdx.x) / G;
-  const int ngroups = gridDim.x * (kThreads / G);
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;      // launched with 256 or 128 threads per block
+  const int ngroups = gridDim.x * (blockDim.x / G);
   if (c.abort && *c.abort) return;
   APR_STEP_ARGS(c, s_param)
   pair_range<G, V>(c, s, gid, ngroups, lane, group_mask<G>(), st);
@@ -1492,7 +1492,11 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
       return APR_OK;
     }
     const bool pairs = V == 1 && c.npair != nullptr;
-    const int grid_pair = std::max(1, std::min((c.B / 2 + gpb - 1) / gpb, sms));
+    // pair blocks hold 128 registers per thread: with 256 threads one block takes half an SM's register file and, next to
+    // the two fast-kernel blocks, leaves no room for a general-stage block until it retires (APR_PAIR_THREADS=128: half)
+    static const int pair_threads = env_int("APR_PAIR_THREADS", 256) == 128 ? 128 : 256;
+    const int gpb_pair = pair_threads / G;
+    const int grid_pair = std::max(1, std::min((c.B / 2 + gpb_pair - 1) / gpb_pair, sms * (kThreads / pair_threads)));
     // Which path gets the SM slots first (experiments, APR_GEN_PRIO bit mask; default 0 = the fast and pair kernels run at
     // the highest stream priority and the general stages, on the caller's stream, take what is left):
     //   bit 0  the three dependent general launches run on a highest-priority stream of their own
@@ -1517,7 +1521,7 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
         APR_CUDA_CHECK(cudaEventRecord(ax.join, fs));
         if (pairs) {
           APR_CUDA_CHECK(cudaStreamWaitEvent(ps, ax.fork, 0));
-          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, kThreads, 0, ps>>>(cc, s);
+          if constexpr (V == 1) pair_kernel<G, V><<<grid_pair, pair_threads, 0, ps>>>(cc, s);
           APR_CUDA_CHECK(cudaEventRecord(ax.join2, ps));
         }
         if (!gen_first && cc.adver) general_stage_kernel<G, V><<<grid_gen, kThreads, 0, gs>>>(cc, s, 0);
