@@ -1494,7 +1494,8 @@ static int run_steps_t(const StepCtx& c, int mode, cudaStream_t st, const StepDy
     const bool pairs = V == 1 && c.npair != nullptr;
     // pair blocks hold 128 registers per thread: with 256 threads one block takes half an SM's register file and, next to
     // the two fast-kernel blocks, leaves no room for a general-stage block until it retires (APR_PAIR_THREADS=128: half)
-    static const int pair_threads = env_int("APR_PAIR_THREADS", 256) == 128 ? 128 : 256;
+    static const int pair_threads_env = env_int("APR_PAIR_THREADS", 256);
+    const int pair_threads = (pair_threads_env == 64 || pair_threads_env == 128) ? pair_threads_env : 256;
     const int gpb_pair = pair_threads / G;
     const int grid_pair = std::max(1, std::min((c.B / 2 + gpb_pair - 1) / gpb_pair, sms * (kThreads / pair_threads)));
     // Which path gets the SM slots first (experiments, APR_GEN_PRIO bit mask; default 0 = the fast and pair kernels run at
