@@ -161,7 +161,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.apr_abi_version() != 1:
+        if L.apr_abi_version() != 2:
             raise RuntimeError("libapr_b200 ABI version mismatch")
         _lib = L
         return _lib

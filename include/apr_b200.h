@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define APR_ABI_VERSION 1
+#define APR_ABI_VERSION 2   /* round 2: apr_train_unique_counts takes the workspace size, new entry points */
 
 enum {
   APR_OK = 0,

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_all_symbols():
     L = ctypes.CDLL(path)
     for name in _declared():
         assert hasattr(L, name), name
-    assert _lib.lib().apr_abi_version() == 1
+    assert _lib.lib().apr_abi_version() == 2
     assert _lib.lib().apr_status_string(3) == b"workspace too small"
 
 
