@@ -274,9 +274,10 @@ class ShardedTrainer(object):
     all on one stream: every rank idled while one prepared G times its own batch and nine NCCL launches shipped the
     result (the serial fraction grew with G).  Here
 
-      * the rank's local triples are all_gathered, the sub-chunk is prepared (rank ``c % G`` for sub-chunk c, so the G
-        ranks prepare different sub-chunks concurrently), its nine regions are PACKED into one staging block, ONE
-        broadcast ships it and the receivers unpack -- all on a low-priority side stream;
+      * the rank's local triples are all_gathered; sub-chunk c (2, 4, ... Sc steps) belongs to rank ``c % G``: every rank
+        first prepares ITS sub-chunks and PACKS their nine regions into one staging block each (the G ranks work at
+        the same time), then ONE broadcast per sub-chunk ships the blocks in order and the receivers unpack -- all on a
+        side stream;
       * the step kernels of sub-chunk c wait only for that sub-chunk's "ready" event, so preparation and exchange of
         sub-chunk c+1 (and of the next call: two workspaces alternate) run under the steps of c;
       * the library issues every launch and cross-rank barrier of the steps (``apr_train_steps_sharded``); the barrier
@@ -299,18 +300,20 @@ class ShardedTrainer(object):
                       "npair": 4, "pairs": 48 * (Bg // 2 + 1)}
         self.regions = [(L[n], step_bytes[n]) for n in self.REGIONS]
         self.bytes_per_step = sum(-(-b // 16) * 16 for _, b in self.regions)
-        self.stage = torch.empty(self.bytes_per_step * self.Sc + 256, dtype=torch.uint8, device=self.dev)
+        self.stage = torch.empty(self.bytes_per_step * self.Sc + 256, dtype=torch.uint8, device=self.dev)   # receive side
+        self.stage_own = []               # packed blocks of this rank's own sub-chunks of one call (grown on demand)
         self.side = torch.cuda.Stream(device=self.dev)
         self.free = [None, None]          # recorded on the main stream after the steps of the call that used workspace k
         self.keep = [None, None]          # the call's global batches (read by the side stream)
         self.calls = 0
 
-    def _pack(self, ws, s0, ns, unpack: bool):
+    def _pack(self, ws, s0, ns, unpack: bool, stage=None):
+        stage = self.stage if stage is None else stage
         o = 0
         for off, sb in self.regions:
             n = sb * ns
             a = ws.buf[off + s0 * sb: off + s0 * sb + n]
-            b = self.stage[o: o + n]
+            b = stage[o: o + n]
             if unpack:
                 a.copy_(b, non_blocking=True)
             else:
@@ -348,25 +351,41 @@ class ShardedTrainer(object):
                     glob.append(xl.contiguous())
             self.keep[k] = glob
             U, I, J = glob
-            for c, s0 in enumerate(range(0, n, self.Sc)):
-                ns = min(self.Sc, n - s0)
-                src = c % self.G
-                if not self.multi or src == self.rank:
-                    # the workspace is addressed by absolute step, the batches by step within this call: same thing here
+            # sub-chunks of 2, 4, ... Sc steps: what the first steps wait for (preparation + exchange of the first
+            # sub-chunk) is kept short; sub-chunk c belongs to rank c % G
+            subs, s0, size = [], 0, min(2, self.Sc)
+            while s0 < n:
+                ns = min(size, n - s0)
+                subs.append((len(subs), s0, ns))
+                s0, size = s0 + ns, min(self.Sc, 2 * size)
+            # phase 1: every rank prepares and packs ITS sub-chunks first, so the G ranks work at the same time
+            mine = {}
+            for c, s0, ns in subs:
+                if not self.multi or c % self.G == self.rank:
                     self._prepare(U, I, J, ws, n, s0, ns)
+                    if self.multi:
+                        slot = len(mine)
+                        while len(self.stage_own) <= slot:
+                            self.stage_own.append(torch.empty_like(self.stage))
+                        self._pack(ws, s0, ns, unpack=False, stage=self.stage_own[slot])
+                        mine[c] = self.stage_own[slot]
+            # phase 2: ONE broadcast per sub-chunk, in order; receivers unpack
+            for c, s0, ns in subs:
                 if self.multi:
+                    src = c % self.G
                     nbytes = self.bytes_per_step * ns
-                    if src == self.rank:
-                        self._pack(ws, s0, ns, unpack=False)
+                    buf = mine[c] if src == self.rank else self.stage
                     gsrc = dist.get_global_rank(self.group, src) if self.group is not None else src
-                    dist.broadcast(self.stage[:nbytes], src=gsrc, group=self.group)
+                    dist.broadcast(buf[:nbytes], src=gsrc, group=self.group)
                     if src != self.rank:
-                        self._pack(ws, s0, ns, unpack=True)
+                        self._pack(ws, s0, ns, unpack=True, stage=self.stage)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 ready.append((s0, ns, ev))
-        for s0, ns, ev in ready:
-            main.wait_event(ev)
+        for c, (s0, ns, ev) in enumerate(ready):
+            # one sub-chunk of look-ahead: the exchange of sub-chunk c+1 is finished before the steps of c start to
+            # compete with it for SMs and links (it only matters at the head of a call: later the side stream is far ahead)
+            main.wait_event(ready[min(c + 1, len(ready) - 1)][2])
             engine.train_steps_sharded(self.t.ptrs, self.G, self.rank, self.d, self.S, self.Bg, lr, reg, reg_adv, eps, adver, ws,
                                        s0, ns, self.t.err, None if stats is None else stats)
         e = torch.cuda.Event()
