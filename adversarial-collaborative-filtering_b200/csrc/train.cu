@@ -61,7 +61,7 @@ static inline int pow2ceil(int x) {
 // Index preparation runs in sub-chunks of `Sc` steps so that its hash tables stay L2-resident (<= ~48 MB).
 struct TrainLayout {
   int S, B, d, Tu, Ti, Sc;
-  int64_t off_hdr, off_GQ, off_HQ, off_GP, off_cbuf, off_ucnt, off_icnt, off_iall, off_nslow, off_nfast, off_tcursor,
+  int64_t off_hdr, off_GQ, off_HQ, off_GP, off_cbuf, off_QN, off_ucnt, off_icnt, off_iall, off_nslow, off_nfast, off_tcursor,
       off_npair, off_seg_slow, off_occ_cnt, off_occ_seg, off_pairs, off_seg_user, off_seg_off, off_seg_cnt, off_ucursor, off_entry, off_rec, off_seg_hdr, off_iu_item, off_tkey_u, off_tval_u,
       off_tkey_i, off_tval_i, total;
 };
@@ -80,6 +80,7 @@ static TrainLayout make_layout(int S, int B, int d) {
   L.off_HQ = take(int64_t(B) * d * 4);         // zero between steps
   L.off_GP = take(int64_t(B) * d * 4);
   L.off_cbuf = take(int64_t(B) * 4);
+  L.off_QN = take(int64_t(B) * 2 * d * 4);     // row-sharded tables: the two item rows of a stage-0 triple, kept for stage 1
   L.off_ucnt = take(int64_t(S) * 4);           // ucnt .. seg_slow are cleared together by prepare
   L.off_icnt = take(int64_t(S) * 4);
   L.off_iall = take(int64_t(S) * 4);
@@ -504,6 +505,7 @@ struct StepCtx {
   const int4* pairs;
   const int4* seg_hdr; const int4* rec; const int32_t* iu_item;
   float* GP; float* cbuf;
+  float* QN;     // [B][2][d]: item rows fetched by stage 0 (row-sharded tables only: stage 1 re-reads them locally, not over NVLink)
   float* stats;  // nullable [S,2]
   const StepDyn* dyn;   // non-null inside a replayed CUDA graph: step = dyn->s + the kernel's step parameter, stats = dyn->stats
   int flags;     // tuning switches (APR_STEP_FLAGS)
@@ -913,6 +915,12 @@ __device__ __forceinline__ void slow_plain(const StepCtx& c, int k0, const int4 
       row_red<G, V>(t, GQ_ROW(c, rc.w), lane, d);
     }
     if (lane == 0) c.cbuf[pos] = cf;
+    if (c.nranks > 1) {
+      // nobody writes these two rows between stage 0 and stage 1 of a step (a shared item row changes in stage 2 only, a
+      // singleton item row only in this segment's own stage 1): stage 1 takes them from the local copy
+      row_store<G, V>(q, c.QN + (int64_t(pos) * 2) * d, lane, d);
+      row_store<G, V>(n, c.QN + (int64_t(pos) * 2 + 1) * d, lane, d);
+    }
   }
   row_store<G, V>(g, c.GP + int64_t(k0) * d, lane, d);
 }
@@ -935,8 +943,8 @@ __device__ __forceinline__ void slow_adv(const StepCtx& c, int k0, const int4 h0
     if (pos > b0) rc = rec[pos];
     const float cf = __ldcg(&c.cbuf[pos]);
     Row<G, V> q, n;
-    row_load<G, V>(q, Q_ROW(c, rc.x), lane, d);
-    row_load<G, V>(n, Q_ROW(c, rc.y), lane, d);
+    row_load<G, V>(q, c.nranks > 1 ? c.QN + (int64_t(pos) * 2) * d : Q_ROW(c, rc.x), lane, d);
+    row_load<G, V>(n, c.nranks > 1 ? c.QN + (int64_t(pos) * 2 + 1) * d : Q_ROW(c, rc.y), lane, d);
     adv_triple<G, V>(c, rc, cf, p, pd, q, n, g, lane, d, mask);
   }
   adagrad_row<G, V>(P_ROW(c, h0.x), AP_ROW(c, h0.x), p, g, lane, d, c.lr);
@@ -1831,6 +1839,7 @@ static int run_range(float* P, float* Q, float* accP, float* accQ, int32_t d, in
   c.iu_item = at<int32_t>(ws, L.off_iu_item);
   c.GP = at<float>(ws, L.off_GP);
   c.cbuf = at<float>(ws, L.off_cbuf);
+  c.QN = at<float>(ws, L.off_QN);
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = s_begin; c.s_end = s_end;
@@ -1986,7 +1995,7 @@ static int stage_sharded_impl(float* const* Pb, float* const* Qb, float* const* 
   c.ucnt = at<int32_t>(ws, L.off_ucnt); c.icnt = at<int32_t>(ws, L.off_icnt); c.nslow = at<int32_t>(ws, L.off_nslow);
   c.npair = pairs_enabled(d) ? at<int32_t>(ws, L.off_npair) : nullptr; c.pairs = at<int4>(ws, L.off_pairs);
   c.seg_hdr = at<int4>(ws, L.off_seg_hdr); c.rec = at<int4>(ws, L.off_rec); c.iu_item = at<int32_t>(ws, L.off_iu_item);
-  c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf);
+  c.GP = at<float>(ws, L.off_GP); c.cbuf = at<float>(ws, L.off_cbuf); c.QN = at<float>(ws, L.off_QN);
   c.stats = stats;
   c.flags = env_int("APR_STEP_FLAGS", 0);
   c.s_begin = step; c.s_end = step + 1; c.only_stage = stage; c.cluster_sync = 0;

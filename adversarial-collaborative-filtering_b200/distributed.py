@@ -274,10 +274,12 @@ class ShardedTrainer(object):
     all on one stream: every rank idled while one prepared G times its own batch and nine NCCL launches shipped the
     result (the serial fraction grew with G).  Here
 
-      * the rank's local triples are all_gathered; sub-chunk c (2, 4, ... Sc steps) belongs to rank ``c % G``: every rank
-        first prepares ITS sub-chunks and PACKS their nine regions into one staging block each (the G ranks work at
-        the same time), then ONE broadcast per sub-chunk ships the blocks in order and the receivers unpack -- all on a
-        side stream;
+      * the ranks' local triples are exchanged (every rank pushes its block into every peer's symmetric-memory staging
+        area); a call is cut into sub-chunks of ceil(n / G) steps (at most Sc) owned round-robin: every rank first prepares
+        ITS sub-chunks and PACKS their nine regions into one block each (the G ranks work at the same time), then pushes
+        the block into every peer's staging slot with plain device-to-device copies over NVLink and announces it through
+        the symmetric-memory signal pad; receivers wait for the signal and unpack -- all on a side stream, no collective
+        kernel (``APR_TRAINER_EXCHANGE=nccl`` selects all_gather + one broadcast per sub-chunk instead);
       * the step kernels of sub-chunk c wait only for that sub-chunk's "ready" event, so preparation and exchange of
         sub-chunk c+1 (and of the next call: two workspaces alternate) run under the steps of c;
       * the library issues every launch and cross-rank barrier of the steps (``apr_train_steps_sharded``); the barrier
@@ -303,9 +305,67 @@ class ShardedTrainer(object):
         self.stage = torch.empty(self.bytes_per_step * self.Sc + 256, dtype=torch.uint8, device=self.dev)   # receive side
         self.stage_own = []               # packed blocks of this rank's own sub-chunks of one call (grown on demand)
         self.side = torch.cuda.Stream(device=self.dev)
+        # Exchange transport.  "symm" (default with peer-mapped tables): the packed block of a sub-chunk and the ranks'
+        # local triples are PUSHED into the peers' symmetric-memory staging slots by plain device-to-device copies and
+        # announced with the symmetric-memory signal pad (put_signal / wait_signal, stream ordered) -- no collective
+        # kernel that has to find free SMs next to step kernels that occupy every one of them (an NCCL broadcast issued
+        # under the running steps can starve until a kernel boundary lets it in).  "nccl": all_gather + broadcast.
+        import os
+        want = os.environ.get("APR_TRAINER_EXCHANGE", "symm")
+        # schedule knobs (measured in DESIGN.md section 6): ramped sub-chunks at the head of a call, owners prepare all
+        # their sub-chunks before the exchange starts, one sub-chunk of look-ahead on the main stream
+        self.ramp = os.environ.get("APR_TRAINER_RAMP", "0") != "0"
+        self.split = os.environ.get("APR_TRAINER_SPLIT", "0") != "0"
+        self.own_first = os.environ.get("APR_TRAINER_ORDER", "own_first") == "own_first"
+        self.lookahead = os.environ.get("APR_TRAINER_LOOKAHEAD", "all")      # "0", "1" (one sub-chunk) or "all"
+        self.exchange = "symm" if (self.multi and want == "symm" and tables.handle is not None) else "nccl"
+        if self.exchange == "symm":
+            import torch.distributed._symmetric_memory as symm_mem
+            self.max_subs = max(len(self._schedule(n)) for n in range(1, self.S + 1))
+            self.slot_bytes = -(-(self.bytes_per_step * self.Sc + 256) // 1024) * 1024
+            self.gather_bytes = -(-(3 * self.S * self.Bl * 4) // 1024) * 1024
+            per_parity = self.max_subs * self.slot_bytes + self.G * self.gather_bytes
+            self.xbuf = symm_mem.empty(2 * per_parity, dtype=torch.uint8, device=self.dev)
+            self.xh = symm_mem.rendezvous(self.xbuf, group if group is not None else dist.group.WORLD)
+            self.per_parity = per_parity
         self.free = [None, None]          # recorded on the main stream after the steps of the call that used workspace k
-        self.keep = [None, None]          # the call's global batches (read by the side stream)
+        # Nothing is allocated after construction: a cudaMalloc of the caching allocator inside a call (the third call of
+        # a run needed fresh blocks for its global batches while the first call's were still held) showed up as sporadic
+        # 10-300 ms stalls of a cold call.  Global batches of a call, per workspace parity:
+        self.glob = [[torch.empty((self.S, self.Bg), dtype=torch.int32, device=self.dev) for _ in range(3)] for _ in range(2)]
+        if self.multi and self.exchange == "nccl":
+            self.loc = torch.empty((self.S, self.Bl), dtype=torch.int32, device=self.dev)
+            self.gbuf = torch.empty((self.G * self.S, self.Bl), dtype=torch.int32, device=self.dev)
+        if self.multi:
+            n_own = max(sum(1 for c, _, _ in self._schedule(n) if (c + k) % self.G == self.rank)
+                        for n in range(1, self.S + 1) for k in range(self.G))
+            self.stage_own = [torch.empty_like(self.stage) for _ in range(max(1, n_own if self.own_first else 1))]
         self.calls = 0
+
+    # symmetric staging layout per call parity k: [max_subs sub-chunk slots][G gather blocks (one per source rank)]
+    def _slot(self, rank, k, c, nbytes):
+        off = k * self.per_parity + c * self.slot_bytes
+        return self.xh.get_buffer(rank, (nbytes,), torch.uint8, off)
+
+    def _gather_block(self, rank, k, src, n):
+        off = k * self.per_parity + self.max_subs * self.slot_bytes + src * self.gather_bytes
+        return self.xh.get_buffer(rank, (3, n, self.Bl), torch.int32, off // 4)
+
+    def _schedule(self, n):
+        """sub-chunks (index, first step, steps) of a call of n steps.  split (default): ceil(n / G) steps each (at most
+        Sc), so that every rank prepares an equal part of the call at the same time; ramp: 2, 4, ... Sc steps; else Sc
+        steps each.  Sub-chunk c of call number k belongs to rank (c + k) % G."""
+        if self.split and self.multi:
+            size = max(1, min(self.Sc, -(-n // self.G)))
+            return [(c, s0, min(size, n - s0)) for c, s0 in enumerate(range(0, n, size))]
+        subs, s0, size = [], 0, (min(2, self.Sc) if self.ramp else self.Sc)
+        while s0 < n:
+            ns = min(size, n - s0)
+            subs.append((len(subs), s0, ns))
+            s0, size = s0 + ns, min(self.Sc, 2 * size)
+        return subs
+
+    SIG_TIMEOUT_MS = 30000   # a peer that never arrives traps after 30 s instead of hanging the GPU
 
     def _pack(self, ws, s0, ns, unpack: bool, stage=None):
         stage = self.stage if stage is None else stage
@@ -340,39 +400,68 @@ class ShardedTrainer(object):
             side.wait_event(inputs_ready)
         ready = []
         with torch.cuda.stream(side):
-            glob = []
-            for x in (u_loc, i_loc, j_loc):
-                xl = x if x.is_cuda else x.to(self.dev, non_blocking=True)
-                if self.multi:
-                    g = torch.empty((self.G * n, self.Bl), dtype=torch.int32, device=self.dev)
-                    dist.all_gather_into_tensor(g, xl.contiguous(), group=self.group)
-                    glob.append(g.view(self.G, n, self.Bl).permute(1, 0, 2).reshape(n, self.Bg).contiguous())
-                else:
-                    glob.append(xl.contiguous())
-            self.keep[k] = glob
-            U, I, J = glob
-            # sub-chunks of 2, 4, ... Sc steps: what the first steps wait for (preparation + exchange of the first
-            # sub-chunk) is kept short; sub-chunk c belongs to rank c % G
-            subs, s0, size = [], 0, min(2, self.Sc)
-            while s0 < n:
-                ns = min(size, n - s0)
-                subs.append((len(subs), s0, ns))
-                s0, size = s0 + ns, min(self.Sc, 2 * size)
-            # phase 1: every rank prepares and packs ITS sub-chunks first, so the G ranks work at the same time
-            mine = {}
-            for c, s0, ns in subs:
-                if not self.multi or c % self.G == self.rank:
-                    self._prepare(U, I, J, ws, n, s0, ns)
+            glob = [g[:n] for g in self.glob[k]]
+            if self.exchange == "symm":
+                # every rank pushes its [3, n, Bl] block into block `rank` of every peer's gather area, then signals
+                mine3 = self._gather_block(self.rank, k, self.rank, n)
+                for q, x in enumerate((u_loc, i_loc, j_loc)):
+                    mine3[q].copy_(x, non_blocking=True)
+                for r in range(self.G):
+                    if r != self.rank:
+                        self._gather_block(r, k, self.rank, n).copy_(mine3, non_blocking=True)
+                        self.xh.put_signal(r, 1, self.SIG_TIMEOUT_MS)
+                for r in range(self.G):
+                    if r != self.rank:
+                        self.xh.wait_signal(r, 1, self.SIG_TIMEOUT_MS)
+                # the G blocks [3, n, Bl] of this rank's gather area (gather_bytes apart) -> global batches [n, G * Bl]
+                off = (k * self.per_parity + self.max_subs * self.slot_bytes) // 4
+                area = self.xh.get_buffer(self.rank, (self.G, self.gather_bytes // 4), torch.int32, off)
+                allb = area[:, :3 * n * self.Bl].view(self.G, 3, n, self.Bl)
+                for q in range(3):
+                    glob[q].view(n, self.G, self.Bl).copy_(allb[:, q].permute(1, 0, 2))
+            else:
+                for q, x in enumerate((u_loc, i_loc, j_loc)):
                     if self.multi:
-                        slot = len(mine)
-                        while len(self.stage_own) <= slot:
-                            self.stage_own.append(torch.empty_like(self.stage))
-                        self._pack(ws, s0, ns, unpack=False, stage=self.stage_own[slot])
-                        mine[c] = self.stage_own[slot]
-            # phase 2: ONE broadcast per sub-chunk, in order; receivers unpack
-            for c, s0, ns in subs:
+                        self.loc[:n].copy_(x, non_blocking=True)
+                        dist.all_gather_into_tensor(self.gbuf[:self.G * n], self.loc[:n], group=self.group)
+                        glob[q].view(n, self.G, self.Bl).copy_(self.gbuf[:self.G * n].view(self.G, n, self.Bl).permute(1, 0, 2))
+                    else:
+                        glob[q].copy_(x, non_blocking=True)
+            U, I, J = glob
+            subs = self._schedule(n)
+            mine = {}
+            owner = lambda c: (c + self.calls) % self.G      # self.calls is the same number on every rank
+
+            def prepare_own(c, s0, ns):
+                self._prepare(U, I, J, ws, n, s0, ns)
                 if self.multi:
-                    src = c % self.G
+                    slot = len(mine) if self.own_first else 0
+                    self._pack(ws, s0, ns, unpack=False, stage=self.stage_own[slot])
+                    mine[c] = self.stage_own[slot]
+
+            # own_first: every rank prepares and packs ITS sub-chunks before the exchange, so the G ranks work at the same
+            # time; else the owner prepares sub-chunk c when its turn comes (the others wait for its block)
+            if self.own_first or not self.multi:
+                for c, s0, ns in subs:
+                    if not self.multi or owner(c) == self.rank:
+                        prepare_own(c, s0, ns)
+            # ONE block per sub-chunk, in order; receivers unpack
+            for c, s0, ns in subs:
+                if self.multi and not self.own_first and owner(c) == self.rank:
+                    prepare_own(c, s0, ns)
+                if self.multi and self.exchange == "symm":
+                    src = owner(c)
+                    nbytes = self.bytes_per_step * ns
+                    if src == self.rank:
+                        for r in range(self.G):
+                            if r != self.rank:
+                                self._slot(r, k, c, nbytes).copy_(mine[c][:nbytes], non_blocking=True)
+                                self.xh.put_signal(r, 2, self.SIG_TIMEOUT_MS)
+                    else:
+                        self.xh.wait_signal(src, 2, self.SIG_TIMEOUT_MS)
+                        self._pack(ws, s0, ns, unpack=True, stage=self._slot(self.rank, k, c, nbytes))
+                elif self.multi:
+                    src = owner(c)
                     nbytes = self.bytes_per_step * ns
                     buf = mine[c] if src == self.rank else self.stage
                     gsrc = dist.get_global_rank(self.group, src) if self.group is not None else src
@@ -383,9 +472,12 @@ class ShardedTrainer(object):
                 ev.record(side)
                 ready.append((s0, ns, ev))
         for c, (s0, ns, ev) in enumerate(ready):
-            # one sub-chunk of look-ahead: the exchange of sub-chunk c+1 is finished before the steps of c start to
-            # compete with it for SMs and links (it only matters at the head of a call: later the side stream is far ahead)
-            main.wait_event(ready[min(c + 1, len(ready) - 1)][2])
+            # "all" (default): the steps of a call start when the WHOLE call is prepared and exchanged on this rank.  In
+            # steady state that costs nothing (the side stream works one call ahead, under the previous call's steps); on a
+            # cold pipeline it keeps the cross-rank signalling of the exchange and the cross-rank barriers of the steps
+            # from running against each other, which measured as sporadic 10-180 ms stalls.
+            ahead = {"0": c, "1": min(c + 1, len(ready) - 1)}.get(self.lookahead, len(ready) - 1)
+            main.wait_event(ready[ahead][2])
             engine.train_steps_sharded(self.t.ptrs, self.G, self.rank, self.d, self.S, self.Bg, lr, reg, reg_adv, eps, adver, ws,
                                        s0, ns, self.t.err, None if stats is None else stats)
         e = torch.cuda.Event()

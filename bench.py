@@ -111,6 +111,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def quiesce_gc():
+    """Called BEFORE the warm-up steps.  A cyclic-GC pass of the interpreter costs tens to hundreds of ms with torch and
+    numpy loaded; one that lands between the warm-up and a 2-6 ms timed region leaves the GPU (clocks, NVLink) idle in
+    front of it, and one inside the region on ONE rank is seen by every rank as a stall at the next cross-rank barrier
+    (both measured).  Collect now, freeze the survivors, keep the collector off while the warm-up
+    and the timed launches are issued; reference counting still frees everything that is not a cycle."""
+    import gc
+    if os.environ.get("APR_BENCH_GC", "off") != "off":
+        return False
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+    return True
+
+
+def resume_gc(was_off):
+    if was_off:
+        import gc
+        gc.enable()
+
+
 def synth_triples(rng, n_steps, batch, users, items):
     u = rng.integers(0, users, size=(n_steps, batch), dtype=np.int32)
     i = rng.integers(0, items, size=(n_steps, batch), dtype=np.int32)
@@ -258,20 +279,26 @@ def main_sharded(args):
         done += n
     warmup_run = done
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("APR_BENCH_NO_SAMPLER") != "1":
         sampler.start()
         time.sleep(0.3)
+    gc_off = quiesce_gc()
     dist.barrier()
     for c in warm:                                          # the timed region follows the warm-up steps directly
         run_chunk(*c)
     trainer.synchronize()
     trainer.check()
-    dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    call_ev = []
+    dist.barrier()
     ev0.record()
     for c in chunks:
         run_chunk(*c)
+        if os.environ.get("APR_BENCH_CALL_TIMES") == "1":   # diagnostic: where inside the timed region the time goes
+            call_ev.append(torch.cuda.Event(enable_timing=True))
+            call_ev[-1].record()
     ev1.record()
+    resume_gc(gc_off)
     trainer.synchronize()
     dist.barrier()
     trainer.check()
@@ -331,6 +358,8 @@ def main_sharded(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfgd, "roofline": roofline, "e2e": e2e, "gpu_launches": K * 8 + 5 * len(chunks), "clocks": clocks,   # per step: fast, pair, 3 stages, 3 barriers
             "warmup_steps_run": warmup_run}
+    if call_ev:
+        line["call_ms"] = [round(a.elapsed_time(b), 3) for a, b in zip([ev0] + call_ev[:-1], call_ev)]
     # ---- second headline metric at N GPUs: item-sharded full-rank evaluation (BASELINE.json configs[4]) ----------
     if not args.no_eval and args.eval_users > 0:
         del t, trainer, last_ws
@@ -415,6 +444,7 @@ def main_single(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    gc_off = quiesce_gc()
     for c in warm:
         run_chunk(*c)
     torch.cuda.synchronize()
@@ -424,6 +454,7 @@ def main_single(args):
     for c in chunks:
         run_chunk(*c)
     ev1.record()
+    resume_gc(gc_off)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None

@@ -28,7 +28,7 @@ def _train_worker(rank, world, port, out):
     from apr_b200 import engine
     from apr_b200.distributed import ShardedTables, train_steps_sharded
     rng = np.random.RandomState(7)
-    U, I, d, S, B = 3001, 1501, 64, 3, 2048
+    U, I, d, S, B = 3001, 1501, 64, (7 if os.environ.get("APR_TEST_TRAINER") == "1" else 3), 2048
     P = (rng.randn(U, d) * 0.1).astype(np.float32)
     Q = (rng.randn(I, d) * 0.1).astype(np.float32)
     u = rng.randint(0, U, (S, B)).astype(np.int32)
@@ -45,13 +45,14 @@ def _train_worker(rank, world, port, out):
     aux = torch.cuda.Stream()
     td = lambda a: torch.from_numpy(a).to(dev)
     if os.environ.get("APR_TEST_TRAINER") == "1":
-        # the pipelined driver: every rank feeds ITS slice of each batch, three calls (both workspaces + a reuse), the
-        # last one shorter than steps_per_call
+        # the pipelined driver: every rank feeds ITS slice of each batch; calls of 4, 1 and 2 steps (both workspaces + a
+        # reuse, several sub-chunks with alternating owners, calls shorter than steps_per_call)
         from apr_b200.distributed import ShardedTrainer
         bl = B // world
-        tr = ShardedTrainer(t, 1, bl)
-        for s in range(S):
-            loc = [td(np.ascontiguousarray(x[s:s + 1, rank * bl:(rank + 1) * bl])) for x in (u, i, j)]
+        tr = ShardedTrainer(t, 4, bl)
+        assert tr.exchange == os.environ.get("APR_TRAINER_EXCHANGE", "symm")
+        for s0, s1 in ((0, 4), (4, 5), (5, 7)):
+            loc = [td(np.ascontiguousarray(x[s0:s1, rank * bl:(rank + 1) * bl])) for x in (u, i, j)]
             tr.train_steps(*loc, 0.05, 0.01, 1.0, 0.5, 1)
         tr.synchronize()
         tr.check()
@@ -91,12 +92,15 @@ def test_row_sharded_training_two_gpus(tmp_path):
 
 
 @pytest.mark.timeout(600)
-def test_row_sharded_training_pipelined_trainer_two_gpus(tmp_path, monkeypatch):
+@pytest.mark.parametrize("exchange,order", [("symm", "own_first"), ("symm", "in_order"), ("nccl", "own_first")])
+def test_row_sharded_training_pipelined_trainer_two_gpus(tmp_path, monkeypatch, exchange, order):
     """ShardedTrainer (all_gather of the ranks' local triples, preparation + ONE packed broadcast per sub-chunk on a side
     stream, alternating workspaces) gives the oracle's result for the same global batches."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     monkeypatch.setenv("APR_TEST_TRAINER", "1")
+    monkeypatch.setenv("APR_TRAINER_EXCHANGE", exchange)
+    monkeypatch.setenv("APR_TRAINER_ORDER", order)
     out = str(tmp_path / "res.pt")
     mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     full, P, Q, u, i, j = torch.load(out, weights_only=False)

@@ -1,0 +1,21 @@
+#!/bin/bash
+# 2 GPUs: collector quiesced before the warm-up
+set -x
+mkdir -p gpurun_out
+run() {  # name steps warmup
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 2 --steps $2 --warmup $3 --no-eval > gpurun_out/r2aa_$1_$2.json 2> gpurun_out/r2aa_$1_$2.err
+  python - $1 $2 <<'PY'
+import json, sys
+try:
+    txt = open("gpurun_out/r2aa_%s_%s.json" % (sys.argv[1], sys.argv[2])).read()
+    j = json.loads([l for l in txt.splitlines() if l.startswith("{")][-1])
+    print("RES %s steps=%s value %.1fM ms/step %.4f e2e %.1fM calls %s" % (sys.argv[1], sys.argv[2], j["value"]/1e6, j["ms_per_step"], j["e2e"]["value"]/1e6, j.get("call_ms")))
+except Exception as e:
+    print("RES %s ERR %s" % (sys.argv[1], e))
+PY
+}
+export APR_BENCH_CALL_TIMES=1
+for k in a b c d; do run gc3_split_$k 20 5; done
+export APR_TRAINER_SPLIT=0
+for k in a b c; do run gc3_nosplit_$k 20 5; done
+unset APR_TRAINER_SPLIT; run gc3_split 256 32
