@@ -307,9 +307,9 @@ class ShardedTrainer(object):
         self.side = torch.cuda.Stream(device=self.dev)
         # Exchange transport.  "symm" (default with peer-mapped tables): the packed block of a sub-chunk and the ranks'
         # local triples are PUSHED into the peers' symmetric-memory staging slots by plain device-to-device copies and
-        # announced with the symmetric-memory signal pad (put_signal / wait_signal, stream ordered) -- no collective
-        # kernel that has to find free SMs next to step kernels that occupy every one of them (an NCCL broadcast issued
-        # under the running steps can starve until a kernel boundary lets it in).  "nccl": all_gather + broadcast.
+        # announced with the symmetric-memory signal pad (put_signal / wait_signal, stream ordered): copy engines and two
+        # one-thread kernels, no collective kernel next to the step kernels, no NCCL call in the loop.  "nccl": all_gather +
+        # one broadcast per sub-chunk (2 GPUs, steady state: 417 M triples/s against 430 M).
         import os
         want = os.environ.get("APR_TRAINER_EXCHANGE", "symm")
         # schedule knobs (measured in DESIGN.md section 6): ramped sub-chunks at the head of a call, owners prepare all
@@ -329,9 +329,10 @@ class ShardedTrainer(object):
             self.xh = symm_mem.rendezvous(self.xbuf, group if group is not None else dist.group.WORLD)
             self.per_parity = per_parity
         self.free = [None, None]          # recorded on the main stream after the steps of the call that used workspace k
-        # Nothing is allocated after construction: a cudaMalloc of the caching allocator inside a call (the third call of
-        # a run needed fresh blocks for its global batches while the first call's were still held) showed up as sporadic
-        # 10-300 ms stalls of a cold call.  Global batches of a call, per workspace parity:
+        # Nothing is allocated after construction.  With per-call tensors the third call of a trainer's life needed a
+        # third set of global batches while the first call's was still held; whether the caching allocator then had to
+        # cudaMalloc (slow and erratic with peer-mapped memory in the process) decided whether a cold 20-step call took
+        # 7.5 or 360 ms.  Global batches of a call, per workspace parity:
         self.glob = [[torch.empty((self.S, self.Bg), dtype=torch.int32, device=self.dev) for _ in range(3)] for _ in range(2)]
         if self.multi and self.exchange == "nccl":
             self.loc = torch.empty((self.S, self.Bl), dtype=torch.int32, device=self.dev)

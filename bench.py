@@ -352,7 +352,8 @@ def main_sharded(args):
     cfgd.update({"batch_per_step": Bg, "batch_per_gpu": Bl, "parallelism": "row-sharded tables over %d GPUs (NVLink peer "
                  "loads/stores/REDs inside the kernels), data-parallel over triples" % world,
                  "step_mode": "fast kernel || pair kernel || general stages, 3 cross-rank barriers per step; index preparation "
-                              "+ one packed broadcast per sub-chunk pipelined on a side stream (ShardedTrainer)",
+                              "+ one packed block per sub-chunk pushed into the peers' symmetric memory, pipelined on a side "
+                              "stream (ShardedTrainer)",
                  "steps_per_call": CH})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
