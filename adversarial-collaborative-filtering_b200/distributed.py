@@ -267,6 +267,23 @@ def train_steps_sharded(tables: ShardedTables, U: torch.Tensor, I: torch.Tensor,
             stream_barrier(group, token)
 
 
+def trainer_schedule(n: int, Sc: int, G: int, ramp: bool = False, split: bool = False):
+    """Sub-chunks (index, first step, steps) of a ShardedTrainer call of n steps, at most Sc steps each (the index
+    preparation's scratch covers Sc steps).  Default: Sc steps each.  split: ceil(n / G) steps each, so that every rank
+    prepares an equal part of the call at the same time; ramp: 2, 4, ... Sc steps.  Sub-chunk c of call number k belongs to
+    rank (c + k) % G.  (Both variants were measured and bring nothing: the head of a cold call is bound by the host
+    issuing the side-stream work)"""
+    if split and G > 1:
+        size = max(1, min(Sc, -(-n // G)))
+        return [(c, s0, min(size, n - s0)) for c, s0 in enumerate(range(0, n, size))]
+    subs, s0, size = [], 0, (min(2, Sc) if ramp else Sc)
+    while s0 < n:
+        ns = min(size, n - s0)
+        subs.append((len(subs), s0, ns))
+        s0, size = s0 + ns, min(Sc, 2 * size)
+    return subs
+
+
 class ShardedTrainer(object):
     """``training_batch`` on row-sharded tables with the index preparation and its exchange taken off the critical path.
 
@@ -353,18 +370,7 @@ class ShardedTrainer(object):
         return self.xh.get_buffer(rank, (3, n, self.Bl), torch.int32, off // 4)
 
     def _schedule(self, n):
-        """sub-chunks (index, first step, steps) of a call of n steps.  split (default): ceil(n / G) steps each (at most
-        Sc), so that every rank prepares an equal part of the call at the same time; ramp: 2, 4, ... Sc steps; else Sc
-        steps each.  Sub-chunk c of call number k belongs to rank (c + k) % G."""
-        if self.split and self.multi:
-            size = max(1, min(self.Sc, -(-n // self.G)))
-            return [(c, s0, min(size, n - s0)) for c, s0 in enumerate(range(0, n, size))]
-        subs, s0, size = [], 0, (min(2, self.Sc) if self.ramp else self.Sc)
-        while s0 < n:
-            ns = min(size, n - s0)
-            subs.append((len(subs), s0, ns))
-            s0, size = s0 + ns, min(self.Sc, 2 * size)
-        return subs
+        return trainer_schedule(n, self.Sc, self.G if self.multi else 1, self.ramp, self.split)
 
     SIG_TIMEOUT_MS = 30000   # a peer that never arrives traps after 30 s instead of hanging the GPU
 

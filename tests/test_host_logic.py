@@ -175,3 +175,23 @@ def test_trainlist_cursor_closed_form_equals_the_sequential_cursor():
         k = np.arange(n)
         closed = np.minimum(k + 1, k + np.minimum.accumulate(a - k))
         assert np.array_equal(closed, sequential(a)), a
+
+
+def test_trainer_schedule_covers_every_step_once():
+    """ShardedTrainer's sub-chunk schedule (host arithmetic): contiguous cover of [0, n), at most Sc steps per sub-chunk,
+    every variant; the staging slots are sized by the longest schedule over all call lengths."""
+    from apr_b200.distributed import trainer_schedule
+    for Sc in (1, 2, 3, 8, 32):
+        for G in (1, 2, 4, 8):
+            for ramp, split in ((False, False), (True, False), (False, True)):
+                longest = max(len(trainer_schedule(n, Sc, G, ramp, split)) for n in range(1, 70))
+                for n in range(1, 70):
+                    subs = trainer_schedule(n, Sc, G, ramp, split)
+                    assert [c for c, _, _ in subs] == list(range(len(subs))) and len(subs) <= longest
+                    pos = 0
+                    for _, s0, ns in subs:
+                        assert s0 == pos and 1 <= ns <= Sc
+                        pos += ns
+                    assert pos == n
+                if not ramp and not split:
+                    assert len(trainer_schedule(64, Sc, G)) == -(-64 // Sc)
