@@ -319,8 +319,8 @@ class ShardedTrainer(object):
                       "npair": 4, "pairs": 48 * (Bg // 2 + 1)}
         self.regions = [(L[n], step_bytes[n]) for n in self.REGIONS]
         self.bytes_per_step = sum(-(-b // 16) * 16 for _, b in self.regions)
-        self.stage = torch.empty(self.bytes_per_step * self.Sc + 256, dtype=torch.uint8, device=self.dev)   # receive side
-        self.stage_own = []               # packed blocks of this rank's own sub-chunks of one call (grown on demand)
+        self.stage_bytes = self.bytes_per_step * self.Sc + 256        # one packed sub-chunk
+        self.stage, self.stage_own = None, []
         self.side = torch.cuda.Stream(device=self.dev)
         # Exchange transport.  "symm" (default with peer-mapped tables): the packed block of a sub-chunk and the ranks'
         # local triples are PUSHED into the peers' symmetric-memory staging slots by plain device-to-device copies and
@@ -339,7 +339,7 @@ class ShardedTrainer(object):
         if self.exchange == "symm":
             import torch.distributed._symmetric_memory as symm_mem
             self.max_subs = max(len(self._schedule(n)) for n in range(1, self.S + 1))
-            self.slot_bytes = -(-(self.bytes_per_step * self.Sc + 256) // 1024) * 1024
+            self.slot_bytes = -(-self.stage_bytes // 1024) * 1024
             self.gather_bytes = -(-(3 * self.S * self.Bl * 4) // 1024) * 1024
             per_parity = self.max_subs * self.slot_bytes + self.G * self.gather_bytes
             self.xbuf = symm_mem.empty(2 * per_parity, dtype=torch.uint8, device=self.dev)
@@ -352,12 +352,15 @@ class ShardedTrainer(object):
         # 7.5 or 360 ms.  Global batches of a call, per workspace parity:
         self.glob = [[torch.empty((self.S, self.Bg), dtype=torch.int32, device=self.dev) for _ in range(3)] for _ in range(2)]
         if self.multi and self.exchange == "nccl":
+            self.stage = torch.empty(self.stage_bytes, dtype=torch.uint8, device=self.dev)        # receive side
             self.loc = torch.empty((self.S, self.Bl), dtype=torch.int32, device=self.dev)
             self.gbuf = torch.empty((self.G * self.S, self.Bl), dtype=torch.int32, device=self.dev)
         if self.multi:
             n_own = max(sum(1 for c, _, _ in self._schedule(n) if (c + k) % self.G == self.rank)
                         for n in range(1, self.S + 1) for k in range(self.G))
-            self.stage_own = [torch.empty_like(self.stage) for _ in range(max(1, n_own if self.own_first else 1))]
+            # packed blocks of this rank's own sub-chunks of one call
+            self.stage_own = [torch.empty(self.stage_bytes, dtype=torch.uint8, device=self.dev)
+                              for _ in range(max(1, n_own if self.own_first else 1))]
         self.calls = 0
 
     # symmetric staging layout per call parity k: [max_subs sub-chunk slots][G gather blocks (one per source rank)]
